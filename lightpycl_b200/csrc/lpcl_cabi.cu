@@ -1,0 +1,385 @@
+// lpcl_cabi.cu - extern "C" boundary of liblightpycl_b200.so (see include/lightpycl_b200.h).
+// Host-side argument validation, scene construction (tile table) and kernel launches.
+// No torch types, no exceptions across the boundary, nothing synchronises the stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/lightpycl_b200.h"
+#include "lpcl_material.cuh"
+
+using namespace lpcl;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) return fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct lpcl_scene {
+    SceneDev dev;
+    void *owned = nullptr;      // one allocation: filter tiles | tile table | materials | vmax
+    int64_t owned_bytes = 0;
+    int sm_count = 148;
+    int device = 0;
+};
+
+static_assert(sizeof(StepCounters) == sizeof(lpcl_step_counters), "counter structs must match");
+
+extern "C" int lpcl_abi_version(void) { return LPCL_ABI_VERSION; }
+extern "C" const char *lpcl_last_error(void) { return g_err; }
+
+static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
+                                 const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
+                                 const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
+                                 void *stream_)
+{
+    if (!out || !d_v0 || !d_v1 || !d_v2 || !h_tri_mesh || !h_mat_type || !h_ior || !h_refl || !h_diss)
+        return fail(LPCL_E_NULL, "lpcl_scene_create: NULL argument");
+    if (tri_count <= 0 || mesh_count <= 0) return fail(LPCL_E_RANGE, "lpcl_scene_create: tri_count/mesh_count must be > 0");
+    if (!aligned16(d_v0) || !aligned16(d_v1) || !aligned16(d_v2))
+        return fail(LPCL_E_ALIGN, "lpcl_scene_create: vertex buffers must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    // tile table: contiguous ascending mesh ids, every mesh non-empty (reference relies on it, cl:262-265)
+    std::vector<TileInfo> tiles;
+    int expect = 0;
+    if (h_tri_mesh[0] != 0) return fail(LPCL_E_MESH_IDS, "mesh ids must start at 0 (got %d)", h_tri_mesh[0]);
+    int start = 0;
+    for (int i = 1; i <= tri_count; ++i) {
+        if (i == tri_count || h_tri_mesh[i] != h_tri_mesh[i - 1]) {
+            if (i < tri_count && h_tri_mesh[i] != h_tri_mesh[i - 1] + 1)
+                return fail(LPCL_E_MESH_IDS, "mesh ids must ascend by 1 (triangle %d: %d after %d)", i, h_tri_mesh[i],
+                            h_tri_mesh[i - 1]);
+            for (int t0 = start; t0 < i; t0 += TILE_TRIS) {
+                TileInfo ti;
+                ti.tri0 = t0;
+                ti.count = (i - t0 < TILE_TRIS) ? (i - t0) : TILE_TRIS;
+                ti.mesh = expect;
+                ti.pad = 0;
+                tiles.push_back(ti);
+            }
+            start = i;
+            ++expect;
+        }
+    }
+    if (expect != mesh_count)
+        return fail(LPCL_E_MESH_IDS, "%d meshes declared but triangles reference %d (empty meshes are not allowed)",
+                    mesh_count, expect);
+
+    lpcl_scene *sc = new lpcl_scene();
+    cudaGetDevice(&sc->device);
+    cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, sc->device);
+    const int n_tiles = (int)tiles.size();
+    const int64_t off_filter = 0;
+    const int64_t off_tiles = align_up(off_filter + (int64_t)n_tiles * TILE_BYTES, 256);
+    const int64_t off_mat = align_up(off_tiles + (int64_t)n_tiles * sizeof(TileInfo), 256);
+    const int64_t off_ior = off_mat + align_up((int64_t)mesh_count * 4, 256);
+    const int64_t off_refl = off_ior + align_up((int64_t)mesh_count * 4, 256);
+    const int64_t off_diss = off_refl + align_up((int64_t)mesh_count * 4, 256);
+    const int64_t off_vmax = off_diss + align_up((int64_t)mesh_count * 4, 256);
+    const int64_t total = off_vmax + 256;
+    cudaError_t e = cudaMalloc(&sc->owned, (size_t)total);
+    if (e != cudaSuccess) {
+        delete sc;
+        return fail((int)e, "cudaMalloc(%lld): %s", (long long)total, cudaGetErrorString(e));
+    }
+    sc->owned_bytes = total;
+    char *base = (char *)sc->owned;
+    SceneDev &d = sc->dev;
+    d.v0 = (const float4 *)d_v0;
+    d.v1 = (const float4 *)d_v1;
+    d.v2 = (const float4 *)d_v2;
+    d.filter = (const float4 *)(base + off_filter);
+    d.tiles = (const TileInfo *)(base + off_tiles);
+    d.mat_type = (const int *)(base + off_mat);
+    d.ior = (const float *)(base + off_ior);
+    d.refl = (const float *)(base + off_refl);
+    d.diss = (const float *)(base + off_diss);
+    d.vmax = (const float *)(base + off_vmax);
+    d.n_tiles = n_tiles;
+    d.tri_count = tri_count;
+    d.mesh_count = mesh_count;
+
+#define SCENE_TRY(expr)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            cudaFree(sc->owned);                                                         \
+            delete sc;                                                                   \
+            return fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__));             \
+        }                                                                                \
+    } while (0)
+    // small host->device copies; the sources are pageable so these complete before returning
+    SCENE_TRY(cudaMemcpyAsync(base + off_tiles, tiles.data(), n_tiles * sizeof(TileInfo), cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemcpyAsync(base + off_mat, h_mat_type, mesh_count * 4, cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemcpyAsync(base + off_ior, h_ior, mesh_count * 4, cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemcpyAsync(base + off_refl, h_refl, mesh_count * 4, cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemcpyAsync(base + off_diss, h_diss, mesh_count * 4, cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemsetAsync(base + off_vmax, 0, 256, stream));
+    unsigned *vmax_bits = (unsigned *)(base + off_vmax + 128);
+    vmax_kernel<<<(tri_count + 255) / 256, 256, 0, stream>>>(d.v0, d.v1, d.v2, tri_count, vmax_bits);
+    vmax_finish_kernel<<<1, 1, 0, stream>>>(vmax_bits, (float *)(base + off_vmax));
+    const long long slots = (long long)n_tiles * TILE_TRIS;
+    build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles,
+                                                                            (float4 *)(base + off_filter));
+    SCENE_TRY(cudaGetLastError());
+    SCENE_TRY(cudaFuncSetAttribute(search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
+    SCENE_TRY(cudaFuncSetAttribute(search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
+    SCENE_TRY(cudaFuncSetAttribute(search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
+#undef SCENE_TRY
+    *out = sc;
+    return 0;
+}
+
+extern "C" void lpcl_scene_destroy(lpcl_scene *scene)
+{
+    if (!scene) return;
+    if (scene->owned) cudaFree(scene->owned);
+    delete scene;
+}
+
+extern "C" int32_t lpcl_scene_tri_count(const lpcl_scene *s) { return s ? s->dev.tri_count : 0; }
+extern "C" int32_t lpcl_scene_mesh_count(const lpcl_scene *s) { return s ? s->dev.mesh_count : 0; }
+extern "C" int64_t lpcl_scene_device_bytes(const lpcl_scene *s) { return s ? s->owned_bytes : 0; }
+
+// scratch layout: key[mesh_count * n] (u64) | cnt[mesh_count * n] (i32), 256-byte aligned parts
+static int64_t scratch_key_bytes(const lpcl_scene *s, int64_t n) { return align_up((int64_t)s->dev.mesh_count * n * 8, 256); }
+static int64_t scratch_cnt_bytes(const lpcl_scene *s, int64_t n) { return align_up((int64_t)s->dev.mesh_count * n * 4, 256); }
+
+extern "C" int64_t lpcl_scratch_bytes(const lpcl_scene *s, int64_t n)
+{
+    if (!s || n < 0) return 0;
+    return scratch_key_bytes(s, n) + scratch_cnt_bytes(s, n) + 256;
+}
+
+static int64_t step_blocks(int64_t n) { return (n + STEP_THREADS - 1) / STEP_THREADS; }
+
+extern "C" int64_t lpcl_step_workspace_bytes(const lpcl_scene *s, int64_t n)
+{
+    if (!s || n < 0) return 0;
+    return lpcl_scratch_bytes(s, n) + align_up(step_blocks(n) * 16 + 16, 256) + 256;
+}
+
+// LPCL_SEARCH_R (1, 2 or 4) and LPCL_SEARCH_CHUNKS override the launch heuristics without rebuilding.
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray_len, void *d_scratch,
+                         unsigned long long *cand_total, cudaStream_t stream)
+{
+    const int64_t n = rays.n;
+    unsigned long long *key = (unsigned long long *)d_scratch;
+    int *cnt = (int *)((char *)d_scratch + scratch_key_bytes(s, n));
+    const long long total = (long long)s->dev.mesh_count * n;
+    const unsigned long long init_key =
+        ((unsigned long long)(*reinterpret_cast<const unsigned *>(&max_ray_len)) << 32) | 0xffffffffull;
+    {
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key);
+    }
+    // rays per thread: 2 by default, fewer when there are too few rays to give every SM two CTAs
+    int R = env_int("LPCL_SEARCH_R", 0); // 1, 2 or 4 forces the variant (tests / tuning)
+    if (R != 1 && R != 2 && R != 4) {
+        R = 2;
+        while (R > 1 && (n + (int64_t)R * SEARCH_THREADS - 1) / ((int64_t)R * SEARCH_THREADS) < (int64_t)s->sm_count * 2) R >>= 1;
+    }
+    const int64_t ray_blocks = (n + (int64_t)R * SEARCH_THREADS - 1) / ((int64_t)R * SEARCH_THREADS);
+    // split the triangle range over blockIdx.y until there are ~8 CTAs per SM in flight
+    int64_t chunks = env_int("LPCL_SEARCH_CHUNKS", 0); // > 0 forces the split (tests / tuning)
+    if (chunks <= 0) {
+        const int64_t want = (int64_t)s->sm_count * 8;
+        chunks = (want + ray_blocks - 1) / ray_blocks;
+    }
+    if (chunks < 1) chunks = 1;
+    if (chunks > s->dev.n_tiles) chunks = s->dev.n_tiles;
+    if (chunks > 65535) chunks = 65535;
+    int tiles_per_chunk = (int)((s->dev.n_tiles + chunks - 1) / chunks);
+    chunks = (s->dev.n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
+    if (R == 4)
+        search_kernel<4><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
+    else if (R == 2)
+        search_kernel<2><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
+    else
+        search_kernel<1><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int check_gen(const lpcl_generation *g, const char *who, bool need_rays)
+{
+    if (!g) return fail(LPCL_E_NULL, "%s: NULL generation", who);
+    if (!g->d_org_pow || !g->d_dir_prev) return fail(LPCL_E_NULL, "%s: NULL ray buffer", who);
+    if (!aligned16(g->d_org_pow) || !aligned16(g->d_dir_prev)) return fail(LPCL_E_ALIGN, "%s: ray buffers must be 16-byte aligned", who);
+    if (need_rays) {
+        if (g->n <= 0 || g->n >= (1LL << 31)) return fail(LPCL_E_RANGE, "%s: n=%lld out of range", who, (long long)g->n);
+        if (g->seg_split < 0 || g->seg_split > g->n) return fail(LPCL_E_RANGE, "%s: seg_split out of range", who);
+        const int64_t second = g->n - g->seg_split;
+        if (g->seg_split > g->capacity || (second > 0 && (g->seg_base < g->seg_split || g->seg_base + second > g->capacity)))
+            return fail(LPCL_E_RANGE, "%s: segments exceed capacity", who);
+    }
+    return 0;
+}
+
+static RaysDev to_dev(const lpcl_generation *g)
+{
+    RaysDev r;
+    r.org_pow = (float4 *)g->d_org_pow;
+    r.dir_prev = (float4 *)g->d_dir_prev;
+    r.lineage = (unsigned long long *)g->d_lineage;
+    r.n = g->n;
+    r.split = g->seg_split;
+    r.base = g->seg_base;
+    return r;
+}
+
+extern "C" int lpcl_intersect(const lpcl_scene *s, const float *d_origin, const float *d_dir, int64_t n,
+                              float max_ray_len, float *d_near_t, int32_t *d_hits, int32_t *d_near_tri, void *d_scratch,
+                              void *stream_)
+{
+    if (!s || !d_origin || !d_dir || !d_near_t || !d_hits || !d_near_tri || !d_scratch)
+        return fail(LPCL_E_NULL, "lpcl_intersect: NULL argument");
+    if (n <= 0 || n >= (1LL << 31)) return fail(LPCL_E_RANGE, "lpcl_intersect: n=%lld out of range", (long long)n);
+    if (!aligned16(d_origin) || !aligned16(d_dir)) return fail(LPCL_E_ALIGN, "lpcl_intersect: ray buffers must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RaysDev rays;
+    rays.org_pow = (float4 *)d_origin; // .w lanes are ignored by the search
+    rays.dir_prev = (float4 *)d_dir;
+    rays.lineage = nullptr;
+    rays.n = n;
+    rays.split = n;
+    rays.base = n;
+    int rc = launch_search(s, rays, max_ray_len, d_scratch, nullptr, stream);
+    if (rc) return rc;
+    const unsigned long long *key = (const unsigned long long *)d_scratch;
+    const int *cnt = (const int *)((char *)d_scratch + scratch_key_bytes(s, n));
+    scratch_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(key, cnt, n, s->dev.mesh_count, d_near_t,
+                                                                          d_hits, d_near_tri);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpcl_intersect_postproc(const lpcl_scene *s, const float *d_origin, const float *d_dir, float *d_dest,
+                                       const int32_t *d_prev_mesh, int32_t *d_n1, int32_t *d_n2, int32_t *d_entering,
+                                       int32_t *d_hit_mesh, int32_t *d_hit_tri, const float *d_near_t,
+                                       const int32_t *d_hits, const int32_t *d_near_tri, int64_t n, float max_ray_len,
+                                       void *stream_)
+{
+    if (!s || !d_origin || !d_dir || !d_dest || !d_prev_mesh || !d_n1 || !d_n2 || !d_entering || !d_hit_mesh ||
+        !d_hit_tri || !d_near_t || !d_hits || !d_near_tri)
+        return fail(LPCL_E_NULL, "lpcl_intersect_postproc: NULL argument");
+    if (n <= 0) return fail(LPCL_E_RANGE, "lpcl_intersect_postproc: n must be > 0");
+    postproc_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        s->dev, (const float4 *)d_origin, (const float4 *)d_dir, (float4 *)d_dest, d_prev_mesh, d_n1, d_n2, d_entering,
+        d_hit_mesh, d_hit_tri, d_near_t, d_hits, d_near_tri, n, max_ray_len);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpcl_reflect_refract_rays(const lpcl_scene *s, const float *d_origin, const float *d_dest,
+                                         const float *d_dir, float *d_power, int32_t *d_measured, const int32_t *d_n1,
+                                         const int32_t *d_n2, float *d_refl_origin, float *d_refl_dir,
+                                         float *d_refl_power, int32_t *d_refl_measured, float *d_refr_origin,
+                                         float *d_refr_dir, float *d_refr_power, int32_t *d_refr_measured,
+                                         const int32_t *d_hit_mesh, const int32_t *d_hit_tri, int64_t n, float ior_env,
+                                         void *stream_)
+{
+    if (!s || !d_origin || !d_dest || !d_dir || !d_power || !d_measured || !d_n1 || !d_n2 || !d_refl_origin ||
+        !d_refl_dir || !d_refl_power || !d_refl_measured || !d_refr_origin || !d_refr_dir || !d_refr_power ||
+        !d_refr_measured || !d_hit_mesh || !d_hit_tri)
+        return fail(LPCL_E_NULL, "lpcl_reflect_refract_rays: NULL argument");
+    if (n <= 0) return fail(LPCL_E_RANGE, "lpcl_reflect_refract_rays: n must be > 0");
+    scatter_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        s->dev, (const float4 *)d_origin, (const float4 *)d_dest, (const float4 *)d_dir, d_power, d_measured, d_n1,
+        d_n2, (float4 *)d_refl_origin, (float4 *)d_refl_dir, d_refl_power, d_refl_measured, (float4 *)d_refr_origin,
+        (float4 *)d_refr_dir, d_refr_power, d_refr_measured, d_hit_mesh, d_hit_tri, n, ior_env);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpcl_pack_rays(const float *d_origin, const float *d_dir, const float *d_power,
+                              const int32_t *d_prev_mesh, int64_t n, int64_t lineage_base, float *d_org_pow,
+                              float *d_dir_prev, uint64_t *d_lineage, void *stream_)
+{
+    if (!d_origin || !d_dir || !d_power || !d_org_pow || !d_dir_prev) return fail(LPCL_E_NULL, "lpcl_pack_rays: NULL argument");
+    if (n <= 0) return fail(LPCL_E_RANGE, "lpcl_pack_rays: n must be > 0");
+    pack_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        (const float4 *)d_origin, (const float4 *)d_dir, d_power, d_prev_mesh, n, lineage_base, (float4 *)d_org_pow,
+        (float4 *)d_dir_prev, (unsigned long long *)d_lineage);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpcl_trace_search(const lpcl_scene *s, const lpcl_generation *parents, void *d_workspace,
+                                 float max_ray_len, lpcl_step_counters *d_counters, void *stream_)
+{
+    if (!s || !d_workspace) return fail(LPCL_E_NULL, "lpcl_trace_search: NULL argument");
+    int rc = check_gen(parents, "lpcl_trace_search(parents)", true);
+    if (rc) return rc;
+    return launch_search(s, to_dev(parents), max_ray_len, d_workspace,
+                         d_counters ? (unsigned long long *)&d_counters->candidates : nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *parents, const lpcl_generation *children,
+                               float *d_dest_meas, int32_t *d_hit, float *d_measured_out, uint64_t *d_measured_lineage,
+                               int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
+                               void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream_)
+{
+    if (!s || !d_dest_meas || !d_counters || !d_workspace) return fail(LPCL_E_NULL, "lpcl_trace_step: NULL argument");
+    int rc = check_gen(parents, "lpcl_trace_step(parents)", true);
+    if (rc) return rc;
+    rc = check_gen(children, "lpcl_trace_step(children)", false);
+    if (rc) return rc;
+    const int64_t n = parents->n;
+    if (children->capacity < 2 * n) return fail(LPCL_E_RANGE, "lpcl_trace_step: children capacity %lld < 2n = %lld",
+                                                (long long)children->capacity, (long long)(2 * n));
+    if (d_measured_out && measured_capacity < measured_base + n)
+        return fail(LPCL_E_RANGE, "lpcl_trace_step: measured buffer too small (%lld < %lld)", (long long)measured_capacity,
+                    (long long)(measured_base + n));
+    if (!aligned16(d_dest_meas) || (d_measured_out && !aligned16(d_measured_out)) || (d_hit && !aligned16(d_hit)))
+        return fail(LPCL_E_ALIGN, "lpcl_trace_step: output buffers must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(lpcl_step_counters), stream));
+    RaysDev par = to_dev(parents), chi = to_dev(children);
+    rc = launch_search(s, par, max_ray_len, d_workspace, (unsigned long long *)&d_counters->candidates, stream);
+    if (rc) return rc;
+
+    char *ws = (char *)d_workspace;
+    const unsigned long long *key = (const unsigned long long *)ws;
+    const int *cnt = (const int *)(ws + scratch_key_bytes(s, n));
+    char *scan = ws + lpcl_scratch_bytes(s, n);
+    const int64_t scan_bytes = align_up(step_blocks(n) * 16 + 16, 256);
+    CUDA_TRY(cudaMemsetAsync(scan, 0, (size_t)scan_bytes, stream));
+    unsigned *ticket = (unsigned *)scan;
+    unsigned long long *words = (unsigned long long *)(scan + 16);
+    step_kernel<<<(unsigned)step_blocks(n), STEP_THREADS, 0, stream>>>(
+        s->dev, par, chi, key, cnt, (float4 *)d_dest_meas, (int4 *)d_hit, (float4 *)d_measured_out,
+        (unsigned long long *)d_measured_lineage, measured_base, measured_capacity, (StepCounters *)d_counters, words, ticket, max_ray_len, ior_env, iteration);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

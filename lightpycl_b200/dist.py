@@ -1,0 +1,126 @@
+"""Ray sharding and the two collectives of the multi-GPU trace loop.
+
+The reference is single-device (one OpenCL queue, iterative_tracer.py:60,74); its only
+partitioning is the <=50,000-ray chunk loop (it:218-273), which shows that rays are
+independent.  Here the ray axis is sharded over one process per GPU:
+
+  * initial rays are split into contiguous blocks (``shard_bounds``), the scene is replicated,
+    children stay on the GPU that produced them - no data-path collective;
+  * per iteration ONE all-reduce of (live ray count, live power) implements the reference's
+    global termination tests (it:372-391) - 16 bytes, latency bound;
+  * at the end ONE padded all-gather of the measured records (x, y, z, power) + lineage
+    implements ``get_measured_rays`` (it:395-411); merging by (iteration, lineage) restores the
+    reference's order, so 1/2/4/8-GPU runs return identical arrays.
+
+All helpers work on CPU tensors with the ``gloo`` backend too (used by the CPU tests).
+"""
+
+from __future__ import annotations
+
+import torch
+
+
+def _td():
+    import torch.distributed as td
+
+    return td
+
+
+def resolve_group(process_group=None):
+    """Return a marker for "distributed is active": the given group, or the string "world" if
+    torch.distributed is initialised, else None (single process)."""
+    td = _td()
+    if process_group is not None:
+        return process_group
+    if td.is_available() and td.is_initialized():
+        return "world"
+    return None
+
+
+def _pg(group):
+    return None if group == "world" else group
+
+
+def world(group):
+    if group is None:
+        return 1, 0
+    td = _td()
+    return td.get_world_size(_pg(group)), td.get_rank(_pg(group))
+
+
+def _comm_device(group, device):
+    """NCCL needs CUDA tensors; gloo works on CPU tensors."""
+    td = _td()
+    backend = str(td.get_backend(_pg(group))).lower()
+    return torch.device(device) if "nccl" in backend else torch.device("cpu")
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous block [lo, hi) of rank ``rank`` out of ``n`` rays (sizes differ by at most 1)."""
+    return (n * rank) // world_size, (n * (rank + 1)) // world_size
+
+
+def all_gather_int(value, group, device):
+    td = _td()
+    ws, _ = world(group)
+    dev = _comm_device(group, device)
+    mine = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    out = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
+    td.all_gather(out, mine, group=_pg(group))
+    return [int(t.item()) for t in out]
+
+
+def all_reduce_sum(value, group, device):
+    td = _td()
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_comm_device(group, device))
+    td.all_reduce(t, op=td.ReduceOp.SUM, group=_pg(group))
+    return float(t.item())
+
+
+def all_reduce_pair(live, power, group, device):
+    """One all-reduce(sum) of {live ray count, live power} (counts are exact in float64 < 2^53)."""
+    td = _td()
+    t = torch.tensor([float(live), float(power)], dtype=torch.float64, device=_comm_device(group, device))
+    td.all_reduce(t, op=td.ReduceOp.SUM, group=_pg(group))
+    return int(round(t[0].item())), float(t[1].item())
+
+
+def merge_measured(records, lineages, iter_ids):
+    """Order records by (iteration, lineage): the reference's get_measured_rays order.
+    Two stable sorts (least-significant key first)."""
+    order = torch.sort(lineages, stable=True).indices
+    order = order[torch.sort(iter_ids[order], stable=True).indices]
+    return records[order], lineages[order], iter_ids[order]
+
+
+def gather_measured(pos_pwr, lineage, per_iter, group, device):
+    """All ranks receive every rank's measured records, merged into the reference order.
+
+    pos_pwr (K,4) f32, lineage (K,) i64, per_iter: this rank's measured count per iteration."""
+    td = _td()
+    ws, _ = world(group)
+    dev = _comm_device(group, device)
+    k = int(pos_pwr.shape[0])
+    iters = torch.repeat_interleave(torch.arange(len(per_iter), dtype=torch.int64),
+                                    torch.tensor(per_iter, dtype=torch.int64)) if len(per_iter) else \
+        torch.zeros(0, dtype=torch.int64)
+    counts = all_gather_int(k, group, device)
+    kmax = max(max(counts), 1)
+    rec = torch.zeros((kmax, 4), dtype=torch.float32, device=dev)
+    lin = torch.zeros(kmax, dtype=torch.int64, device=dev)
+    itr = torch.zeros(kmax, dtype=torch.int64, device=dev)
+    if k:
+        rec[:k] = pos_pwr.to(dev)
+        lin[:k] = lineage.to(dev)
+        itr[:k] = iters.to(dev)
+    recs = [torch.zeros_like(rec) for _ in range(ws)]
+    lins = [torch.zeros_like(lin) for _ in range(ws)]
+    itrs = [torch.zeros_like(itr) for _ in range(ws)]
+    td.all_gather(recs, rec, group=_pg(group))
+    td.all_gather(lins, lin, group=_pg(group))
+    td.all_gather(itrs, itr, group=_pg(group))
+    rec_all = torch.cat([r[:c] for r, c in zip(recs, counts)], dim=0)
+    lin_all = torch.cat([r[:c] for r, c in zip(lins, counts)], dim=0)
+    itr_all = torch.cat([r[:c] for r, c in zip(itrs, counts)], dim=0)
+    merged, _, _ = merge_measured(rec_all, lin_all, itr_all)
+    return merged

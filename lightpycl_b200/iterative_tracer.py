@@ -1,0 +1,505 @@
+"""The trace loop: drop-in for the reference's ``iterative_tracer.CL_Tracer`` on B200.
+
+Reference: iterative_tracer.py:32-411 ("it:").  Same class name, constructor and method
+signatures and the same result structure; the body is new.  Where the reference uploads rays,
+launches three OpenCL kernels, downloads 12 arrays and prunes with NumPy on every iteration
+(it:261-375), this loop keeps every ray generation in HBM as torch tensors and drives the
+sm_100a kernels of ``liblightpycl_b200.so`` through the C ABI (``_cabi``): one search kernel
+plus one fused resolve/Fresnel/compaction kernel per generation, and a 64-byte counter
+read-back per iteration for the reference's two termination tests (it:372-391).
+
+Multi-GPU (one process per GPU, ``torch.distributed``): rays are sharded contiguously over the
+ranks, the scene is replicated, children stay on the GPU that produced them.  The only
+collectives are a per-iteration all-reduce of (live rays, live power) and the final gather of
+measured rays; see ``dist.py``.
+
+There is no CPU fallback: constructing a ``CL_Tracer`` without the CUDA extension or without a
+CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pickle
+from time import strftime, time
+
+import numpy as np
+
+from . import _cabi
+from . import dist as _dist
+
+__all__ = ["CL_Tracer", "TraceResults"]
+
+
+# ------------------------------------------------------------------------------------------ host-side flattening
+def flatten_light_sources(light_source):
+    """it:99-118.  Returns (origin (N,4) f32, dir (N,4) f32, power f32 in the sources' shape)."""
+    origins, dirs, powers = [], [], []
+    for light in light_source:
+        o = np.asarray(light.rays_origin, dtype=np.float32)
+        d = np.asarray(light.rays_dir, dtype=np.float32)
+        p = np.asarray(light.rays_power, dtype=np.float32)
+        if len(o) != int(light.ray_count) or len(d) != int(light.ray_count):
+            raise ValueError("light source arrays do not match ray_count")
+        origins.append(o.reshape(-1, 4))
+        dirs.append(d.reshape(-1, 4))
+        powers.append(p)
+    if not origins:
+        raise ValueError("light_source must be a non-empty list of sources")
+    shapes = {p.ndim for p in powers}
+    if len(shapes) != 1:  # np.append(..., axis=0) of (N,1) and (N,) raises in the reference too (it:111)
+        raise ValueError("all light sources must give rays_power with the same number of dimensions")
+    origin = np.ascontiguousarray(np.concatenate(origins, axis=0))
+    direc = np.ascontiguousarray(np.concatenate(dirs, axis=0))
+    power = np.ascontiguousarray(np.concatenate(powers, axis=0))
+    return origin, direc, power
+
+
+def sorted_sequential_sum_f32(p):
+    """``sum(np.sort(p))`` as the reference evaluates it (it:115): sort along the last axis, then
+    a left-to-right float32 accumulation (np.cumsum accumulates sequentially)."""
+    flat = np.sort(np.asarray(p, dtype=np.float32)).reshape(-1)
+    if flat.size == 0:
+        return np.float32(0.0)
+    return np.float32(np.cumsum(flat, dtype=np.float32)[-1])
+
+
+def flatten_meshes(meshes):
+    """it:121-151.  Returns dict(v0, v1, v2 (T,4) f32, tri_mesh (T,) i32, mat_type i32, ior, refl, diss f32)."""
+    m = len(meshes)
+    if m == 0:
+        raise ValueError("meshes must be a non-empty list")
+    mat_type = np.zeros(m, dtype=np.int32)
+    ior = np.zeros(m, dtype=np.float32)
+    refl = np.zeros(m, dtype=np.float32)
+    diss = np.zeros(m, dtype=np.float32)
+    v0s, v1s, v2s, ids = [], [], [], []
+    for j, mesh in enumerate(meshes):
+        mat = mesh.getMaterialBuf()
+        mat_type[j] = np.int32(mat.get("type"))
+        ior[j] = np.float32(mat.get("IOR"))
+        refl[j] = np.float32(mat.get("R"))
+        diss[j] = np.float32(mat.get("dissipation"))
+        tb = mesh.tribuf()
+        a = np.asarray(tb[0], dtype=np.float32).reshape(-1, 4)
+        if len(a) == 0:
+            raise ValueError("mesh %d has no triangles (the reference kernel requires non-empty meshes)" % j)
+        v0s.append(a)
+        v1s.append(np.asarray(tb[1], dtype=np.float32).reshape(-1, 4))
+        v2s.append(np.asarray(tb[2], dtype=np.float32).reshape(-1, 4))
+        ids.append(np.full(len(a), j, dtype=np.int32))
+    return dict(v0=np.ascontiguousarray(np.concatenate(v0s)), v1=np.ascontiguousarray(np.concatenate(v1s)),
+                v2=np.ascontiguousarray(np.concatenate(v2s)), tri_mesh=np.ascontiguousarray(np.concatenate(ids)),
+                mat_type=mat_type, ior=ior, refl=refl, diss=diss)
+
+
+# ------------------------------------------------------------------------------------------ device-side state
+class _Generation:
+    """One ray generation in HBM (packed layout of include/lightpycl_b200.h)."""
+
+    __slots__ = ("org_pow", "dir_prev", "lineage", "n", "split", "base")
+
+    def __init__(self, org_pow, dir_prev, lineage, n, split, base):
+        self.org_pow, self.dir_prev, self.lineage = org_pow, dir_prev, lineage
+        self.n, self.split, self.base = int(n), int(split), int(base)
+
+    def c_struct(self):
+        g = _cabi.Generation()
+        g.d_org_pow = self.org_pow.data_ptr()
+        g.d_dir_prev = self.dir_prev.data_ptr()
+        g.d_lineage = self.lineage.data_ptr() if self.lineage is not None else None
+        g.n, g.seg_split, g.seg_base = self.n, self.split, self.base
+        g.capacity = self.org_pow.shape[0]
+        return g
+
+    def logical(self, t):
+        """Logical-order view (copy only when the generation has two segments)."""
+        import torch
+
+        if self.split == self.n:
+            return t[: self.n]
+        return torch.cat((t[: self.split], t[self.base: self.base + (self.n - self.split)]), dim=0)
+
+
+class TraceResults:
+    """``self.results`` of the reference (it:355,393): a list with one tuple per iteration,
+    ``(rays_origin (n,4) f32, rays_dest (n,4) f32, rays_pow f32, rays_meas (n,) i32)``.
+
+    The data stays in HBM; an entry is downloaded and converted to NumPy the first time it is
+    indexed or iterated.  ``ray_counts`` gives ``len(res[3])`` per iteration without any
+    download.  Iteration 0's power keeps the light sources' shape, e.g. (N,1).
+    """
+
+    def __init__(self):
+        self._dev = []  # (generation, dest_meas tensor, power shape or None)
+        self._host = {}
+        self.ray_counts = []
+
+    def _append(self, gen, dest_meas, pow_shape):
+        self._dev.append((gen, dest_meas, pow_shape))
+        self.ray_counts.append(gen.n)
+
+    def __len__(self):
+        return len(self._dev)
+
+    def _materialise(self, k):
+        if k not in self._host:
+            gen, dest_meas, pow_shape = self._dev[k]
+            op = gen.logical(gen.org_pow).cpu().numpy()
+            dm = dest_meas.cpu().numpy()
+            origin = np.ascontiguousarray(op.copy())
+            power = np.ascontiguousarray(origin[:, 3].copy())
+            origin[:, 3] = 0.0
+            dest = np.ascontiguousarray(dm.copy())
+            meas = np.ascontiguousarray(dest[:, 3].copy()).view(np.int32)
+            dest[:, 3] = 0.0
+            if pow_shape is not None:
+                power = power.reshape(pow_shape)
+            self._host[k] = (origin, dest, power, meas)
+        return self._host[k]
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._materialise(i) for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        return self._materialise(k)
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self._materialise(k)
+
+
+class CL_Tracer:
+    """B200 trace engine with the reference's ``CL_Tracer`` interface (it:32-411).
+
+    ``platform_name`` / ``device_name`` are accepted for source compatibility (it:36); the CUDA
+    device is ``device`` if given, else ``cuda:$LOCAL_RANK`` (or the current device).
+
+    Extra keyword arguments (all optional, defaults keep the reference's behaviour):
+      keep_results   retain every generation for ``self.results`` (default True, like it:355);
+                     False keeps only the measured-ray buffer (for runs that would not fit).
+      record_hits    also retain per-ray (hit mesh, hit triangle, n1, n2) in ``self.hit_records``.
+      lineage        carry a 64-bit lineage id per ray (auto-enabled when world_size > 1).
+      process_group  torch.distributed group to shard over (default: the world group if
+                     torch.distributed is initialised).
+      shard_input    True: every rank passes the SAME sources and traces its contiguous slice;
+                     False: every rank passes its OWN rays (used by bench.py weak scaling).
+    """
+
+    results = None
+    geometry = None
+
+    def __init__(self, platform_name="NVIDIA", device_name="770", debug=False, device=None, keep_results=True,
+                 record_hits=False, lineage=None, process_group=None, shard_input=True, verbose=False):
+        import torch
+
+        self.debug = debug
+        self.verbose = verbose or debug
+        self._torch = torch
+        self._lib = _cabi.load()  # raises if the CUDA extension is missing: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("lightpycl_b200.CL_Tracer needs a CUDA device (B200, sm_100a); none is visible")
+        if device is None:
+            device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.platform_name, self.device_name = platform_name, device_name
+        if self.verbose:
+            print("Using CUDA device: ", torch.cuda.get_device_name(self.device))
+        self.keep_results = keep_results
+        self.record_hits = record_hits
+        self._group = _dist.resolve_group(process_group)
+        self.world_size, self.rank = _dist.world(self._group)
+        self._lineage = bool(lineage) if lineage is not None else self.world_size > 1
+        self.shard_input = shard_input
+        self._scene = None
+        self._scene_tensors = None
+        self._workspace = None
+        self.timings = {}
+        self.stats = {}
+
+    # ---------------------------------------------------------------------------------- scene
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _release_scene(self):
+        if self._scene is not None:
+            self._lib.lpcl_scene_destroy(self._scene)
+            self._scene = None
+            self._scene_tensors = None
+
+    def __del__(self):
+        try:
+            self._release_scene()
+        except Exception:
+            pass
+
+    def _upload_scene(self, flat):
+        torch = self._torch
+        self._release_scene()
+        dev = {k: torch.from_numpy(flat[k]).to(self.device, non_blocking=False) for k in ("v0", "v1", "v2")}
+        handle = C.c_void_p()
+        rc = self._lib.lpcl_scene_create(
+            C.byref(handle), dev["v0"].data_ptr(), dev["v1"].data_ptr(), dev["v2"].data_ptr(),
+            flat["tri_mesh"].ctypes.data, len(flat["tri_mesh"]), flat["mat_type"].ctypes.data, flat["ior"].ctypes.data,
+            flat["refl"].ctypes.data, flat["diss"].ctypes.data, len(flat["mat_type"]), self._stream())
+        _cabi.check(rc, "lpcl_scene_create")
+        self._scene = handle
+        self._scene_tensors = dev  # the handle borrows the vertex buffers: keep them alive
+
+    def _get_workspace(self, n):
+        torch = self._torch
+        need = int(self._lib.lpcl_step_workspace_bytes(self._scene, n))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # ---------------------------------------------------------------------------------- the loop
+    def iterative_tracer(self, light_source, meshes, trace_iterations=100, trace_until_dissipated=0.99,
+                         max_ray_len=np.float32(1e3), ior_env=np.float32(1.0)):
+        """Trace ``light_source`` (list of sources) through ``meshes`` (list of GeoObject-like).
+
+        Same contract as the reference (it:77-393): repeat intersect -> resolve media -> Fresnel
+        split -> prune, until ``trace_iterations`` generations were processed, the surviving
+        power falls below ``(1 - trace_until_dissipated) * input_power`` or no ray is left.
+        Returns and stores ``self.results``; also sets ``self.tri_count``, ``self.meshes`` and
+        ``self.geometry`` like the reference (it:152-158).
+        """
+        torch = self._torch
+        lib = self._lib
+        t_start = time()
+        max_ray_len = np.float32(max_ray_len)
+        ior_env = np.float32(ior_env)
+
+        origin, direc, power = flatten_light_sources(light_source)
+        flat = flatten_meshes(meshes)
+        self.tri_count = np.int32(len(flat["v0"]))
+        self.mesh_count = np.int32(len(flat["mat_type"]))
+        self.meshes = meshes
+        self.geometry = (flat["v0"], flat["v1"], flat["v2"])
+        if self.verbose:
+            print("Triangle count:              ", self.tri_count)
+            print("Mesh count:                  ", self.mesh_count)
+
+        # shard the rays over the ranks (contiguous blocks keep the reference order inside a rank)
+        n_all = len(origin)
+        if self.world_size > 1 and self.shard_input:
+            lo, hi = _dist.shard_bounds(n_all, self.world_size, self.rank)
+            input_power = float(sorted_sequential_sum_f32(power))
+            origin, direc, power_local = origin[lo:hi], direc[lo:hi], power.reshape(n_all, -1)[lo:hi]
+            lineage_base = lo
+            pow_shape = None if power.ndim == 1 else (hi - lo,) + power.shape[1:]
+            power = power_local
+        else:
+            input_power = float(sorted_sequential_sum_f32(power))
+            lineage_base = 0
+            pow_shape = None if power.ndim == 1 else power.shape
+            if self.world_size > 1:  # every rank brought its own rays
+                counts = _dist.all_gather_int(len(origin), self._group, self.device)
+                lineage_base = int(sum(counts[: self.rank]))
+                input_power = _dist.all_reduce_sum(input_power, self._group, self.device)
+        self.input_power = input_power
+
+        with torch.cuda.device(self.device):
+            self._upload_scene(flat)
+            n = len(origin)
+            results = TraceResults()
+            self.results = results
+            self.hit_records = []
+            self._measured = None
+            self._measured_lineage = None
+            self._measured_count = 0
+            self._measured_per_iter = []
+            self.stats = dict(rays=[], live=[], power_left=[], candidates=[], measured=[], terminated=[])
+            counters_dev = torch.zeros(8, dtype=torch.int64, device=self.device)
+            counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+
+            gen = None
+            if n > 0:
+                o_d = torch.from_numpy(origin).to(self.device)
+                d_d = torch.from_numpy(direc).to(self.device)
+                p_d = torch.from_numpy(np.ascontiguousarray(power.reshape(-1))).to(self.device)
+                org_pow = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+                dir_prev = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+                lineage = torch.empty(n, dtype=torch.int64, device=self.device) if self._lineage else None
+                rc = lib.lpcl_pack_rays(o_d.data_ptr(), d_d.data_ptr(), p_d.data_ptr(), None, n, lineage_base,
+                                        org_pow.data_ptr(), dir_prev.data_ptr(),
+                                        lineage.data_ptr() if lineage is not None else None, self._stream())
+                _cabi.check(rc, "lpcl_pack_rays")
+                gen = _Generation(org_pow, dir_prev, lineage, n, n, n)
+                del o_d, d_d, p_d
+
+            for t_iter in range(int(trace_iterations)):
+                n = gen.n if gen is not None else 0
+                if self.verbose:
+                    print("ITERATION", t_iter + 1, "with ", n, "rays.")
+                c = dict(n_reflect=0, n_refract=0, n_measured=0, n_terminated=0, live_power=0.0, measured_power=0.0,
+                         candidates=0)
+                children = None
+                if n > 0:
+                    cap = 2 * n
+                    ch_org = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
+                    ch_dir = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
+                    ch_lin = torch.empty(cap, dtype=torch.int64, device=self.device) if self._lineage else None
+                    children = _Generation(ch_org, ch_dir, ch_lin, 0, 0, n)
+                    dest_meas = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+                    hit = torch.empty((n, 4), dtype=torch.int32, device=self.device) if self.record_hits else None
+                    self._reserve_measured(self._measured_count + n)
+                    ws = self._get_workspace(n)
+                    pg, cg = gen.c_struct(), children.c_struct()
+                    rc = lib.lpcl_trace_step(
+                        self._scene, C.byref(pg), C.byref(cg), dest_meas.data_ptr(),
+                        hit.data_ptr() if hit is not None else None, self._measured.data_ptr(),
+                        self._measured_lineage.data_ptr() if self._measured_lineage is not None else None,
+                        self._measured_count, self._measured.shape[0], counters_dev.data_ptr(), ws.data_ptr(),
+                        C.c_float(max_ray_len), C.c_float(ior_env), t_iter, self._stream())
+                    _cabi.check(rc, "lpcl_trace_step")
+                    counters_host.copy_(counters_dev, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    sc = _cabi.StepCounters.from_buffer_copy(counters_host.numpy().tobytes())
+                    c = {k: getattr(sc, k) for k, _ in _cabi.StepCounters._fields_}
+                    children.n = c["n_reflect"] + c["n_refract"]
+                    children.split = c["n_reflect"]
+                    if self.keep_results:
+                        results._append(gen, dest_meas, pow_shape if t_iter == 0 else None)
+                    else:
+                        results.ray_counts.append(n)
+                    if self.record_hits:
+                        self.hit_records.append(hit)
+                    self._measured_count += c["n_measured"]
+                    self._measured_per_iter.append(c["n_measured"])
+                elif self.keep_results:
+                    empty = torch.zeros((0, 4), dtype=torch.float32, device=self.device)
+                    results._append(_Generation(empty, empty, None, 0, 0, 0), empty, pow_shape if t_iter == 0 else None)
+                    self._measured_per_iter.append(0)
+
+                # it:372-391, evaluated over ALL ranks
+                live, power_left = c["n_reflect"] + c["n_refract"], c["live_power"]
+                if self.world_size > 1:
+                    live, power_left = _dist.all_reduce_pair(live, power_left, self._group, self.device)
+                for k, v in (("rays", n), ("live", live), ("power_left", power_left), ("candidates", c["candidates"]),
+                             ("measured", c["n_measured"]), ("terminated", c["n_terminated"])):
+                    self.stats[k].append(v)
+                gen = children if (children is not None and children.n > 0) else None
+                if self.verbose:
+                    print("Power left in scene:           ", power_left / input_power * 100.0 if input_power else 0.0)
+                if power_left < (1.0 - float(trace_until_dissipated)) * input_power:
+                    break
+                if live == 0:
+                    break
+        self.timings["iterative_tracer_s"] = time() - t_start
+        return self.results
+
+    def _reserve_measured(self, need):
+        torch = self._torch
+        cap = 0 if self._measured is None else self._measured.shape[0]
+        if cap >= need:
+            return
+        new_cap = max(need, int(cap * 1.5), 1024)
+        buf = torch.empty((new_cap, 4), dtype=torch.float32, device=self.device)
+        lin = torch.empty(new_cap, dtype=torch.int64, device=self.device) if self._lineage else None
+        if self._measured is not None and self._measured_count:
+            buf[: self._measured_count] = self._measured[: self._measured_count]
+            if lin is not None:
+                lin[: self._measured_count] = self._measured_lineage[: self._measured_count]
+        self._measured, self._measured_lineage = buf, lin
+
+    # ---------------------------------------------------------------------------------- results
+    def get_measured_rays(self, gather=True):
+        """it:395-411: ``(pos (K,4) f32, pwr (K,) f32)`` of every ray that ended on a measure
+        surface, iteration-major, ray order inside an iteration.  Read from the per-GPU
+        measured-ray buffer the step kernel appends to (no pass over ``self.results``).
+
+        With world_size > 1 and ``gather=True`` every rank returns the merged global arrays in
+        the reference order (records are merged by (iteration, lineage))."""
+        pos_pwr = self.measured_device()
+        per_iter = list(self._measured_per_iter)
+        if self.world_size > 1 and gather:
+            pos_pwr = _dist.gather_measured(pos_pwr, self._measured_lineage[: self._measured_count], per_iter,
+                                            self._group, self.device)
+        rec = pos_pwr.cpu().numpy()
+        pos = np.ascontiguousarray(rec.copy())
+        pwr = np.ascontiguousarray(pos[:, 3].copy())
+        pos[:, 3] = 0.0
+        if len(self._measured_per_iter) == 1 and self.results is not None and len(self.results._dev) == 1 \
+                and self.results._dev[0][2] is not None:
+            pwr = pwr.reshape((-1,) + tuple(self.results._dev[0][2][1:]))  # it:406: no flatten for k == 0
+        return (pos, pwr)
+
+    def measured_device(self):
+        """The measured-ray records of THIS GPU as a (K,4) float32 CUDA tensor (x, y, z, power)."""
+        torch = self._torch
+        if self._measured is None:
+            return torch.zeros((0, 4), dtype=torch.float32, device=self.device)
+        return self._measured[: self._measured_count]
+
+    def get_binned_data(self, limits=((-10, 10), (-10, 10)), points=500):
+        """it:413-418: 2-D histogram of measured end points (x, y) weighted by power."""
+        (pos, pwr) = self.get_measured_rays()
+        (H, x_coord, y_coord) = np.histogram2d(x=pos[:, 0], y=pos[:, 1], bins=points, range=limits,
+                                               weights=np.asarray(pwr).reshape(-1))
+        self.hist_data = (H, x_coord, y_coord)
+        return self.hist_data
+
+    def _projected(self, kind, rot=None):
+        from . import projection
+
+        (pos, pwr) = self.get_measured_rays()
+        return projection.project(kind, pos, np.asarray(pwr).reshape(-1), rot)
+
+    def get_binned_data_stereographic(self, limits=((-1, 1), (-1, 1)), points=500):
+        """it:503-531."""
+        x, y, pwr = self._projected("stereographic")
+        return self._bin(x, y, pwr, limits, points)
+
+    def get_binned_data_angular(self, limits=((-1, 1), (-1, 1)), points=500):
+        """it:534-562."""
+        x, y, pwr = self._projected("angular")
+        return self._bin(x, y, pwr, limits, points)
+
+    def _bin(self, x, y, pwr, limits, points):
+        dx = np.float64(limits[0][1] - limits[0][0]) / np.float64(points)
+        dy = np.float64(limits[1][1] - limits[1][0]) / np.float64(points)
+        w = np.float64(pwr) / (dx * dy)  # it:553-558
+        (H, x_coord, y_coord) = np.histogram2d(x=x.flatten(), y=y.flatten(), bins=points, range=limits,
+                                               weights=w.flatten())
+        self.hist_data = (H, x_coord, y_coord)
+        return self.hist_data
+
+    # ---------------------------------------------------------------------------------- persistence
+    def pickle_results(self):
+        """it:711-733: dump (results, meshes) to ./<timestamp>-tracer_results.txt."""
+        try:
+            payload = pickle.dumps((list(self.results), self.meshes), 1)
+            fname = "./{0}-tracer_results.txt".format(strftime("%Y.%m.%d.%H.%M.%S"))
+            with open(fname, "wb") as f:
+                f.write(payload)
+        except Exception:
+            print("Pickling results failed.")
+            return None
+        print("Pickled results and meshes to ", fname)
+        return fname
+
+    def load_pickle_results(self, path):
+        """it:735-751."""
+        try:
+            with open(path, "rb") as f:
+                (self.results, self.meshes) = pickle.loads(f.read())
+        except Exception:
+            print("UnPickling results failed.")
+        else:
+            print("UnPickled results and meshes from ", path)
+
+    def save_traced_scene(self, dxf_file):
+        """it:754-779: rays and geometry as DXF 3DFACE entities (dependency-free writer)."""
+        from ._dxf import write_faces
+
+        o = np.concatenate([r[0][:, :3] for r in self.results]) if len(self.results) else np.zeros((0, 3))
+        d = np.concatenate([r[1][:, :3] for r in self.results]) if len(self.results) else np.zeros((0, 3))
+        (v0, v1, v2) = self.geometry
+        write_faces(dxf_file, [("Rays", 3, o, d, d), ("Geometry", 5, v0[:, :3], v1[:, :3], v2[:, :3])])

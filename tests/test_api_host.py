@@ -1,0 +1,129 @@
+"""Host-side API shell: generators, light sources, flattening, C-ABI symbol table.  No GPU."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lightpycl_b200 import _cabi, dist, geo_optical_elements as goe, light_source as lsm, scenes
+from lightpycl_b200 import iterative_tracer as it
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_triangle_counts_match_survey():
+    oe = goe.optical_elements()
+    assert len(oe.cube((0, 0, 0, 0), [1, 1, 1, 0]).triangles) == 12
+    assert len(oe.hemisphere([0, 0, 0, 0], 10.0).triangles) == 2 * 71 * 73
+    assert len(oe.sphere([0, 0, 0, 0], 10.0).triangles) == 2 * 71 * 73
+    assert len(oe.parabolic_mirror().triangles) == 2 * 199 * 73
+    assert len(oe.lens_spherical_biconcave((0, 0, 0), 60.0, 6000.0, 50.0, 2.5).triangles) == 2 * 120 * 36
+    assert len(oe.spherical_lens_nofoc(7.8, 6.5, 0.0, 0.55, 5.0).triangles) == 2 * 99 * 72
+    for name, want in (("c2_directivity_lens", 19006), ("c3_parabolic_mirror", 100552), ("c4_human_eye", 67390)):
+        _, meshes, _ = scenes.CONFIGS[name](ray_count=4)
+        assert sum(len(m.triangles) for m in meshes) == want
+
+
+def test_revolve_curve_matches_loop_definition():
+    """Vectorised revolve_curve == the per-vertex construction of reference geo:285-300."""
+    curve = [[0.0, 0.0], [1.0, 2.0], [3.0, 2.5], [4.0, 0.5]]
+    ang, ang_pts = np.pi, 5
+    mesh = goe.optical_elements().revolve_curve(curve, axis="x", ang=ang, ang_pts=ang_pts)
+    d_ang = ang / (ang_pts - 1.0)
+    angs = np.linspace(0.0, ang - d_ang, ang_pts)
+    verts, tris = [], []
+    for k, (p1, p2) in enumerate(zip(angs, angs + d_ang)):
+        for i in range(len(curve) - 1):
+            for phi, c in ((p1, curve[i]), (p1, curve[i + 1]), (p2, curve[i]), (p2, curve[i + 1])):
+                verts.append(np.array([c[0], np.cos(phi) * c[1], np.sin(phi) * c[1], 0], dtype=np.float32))
+            base = i * 4 + 4 * k * (len(curve) - 1)
+            tris += [[base, base + 1, base + 2], [base + 2, base + 3, base + 1]]
+    assert np.array_equal(np.asarray(mesh.vertices), np.array(verts))
+    assert np.array_equal(np.asarray(mesh.triangles), np.array(tris))
+
+
+def test_material_quirks():
+    m = goe.optical_elements().cube((0, 0, 0, 0), [1, 1, 1, 0])
+    m.setMaterial(mat_type="mirror", reflectivity=0.5)  # Q2: reflectivity is NOT stored
+    assert m.getMaterialBuf() == {"type": 1, "IOR": 1.0, "R": 1.0, "dissipation": 0.0}
+    m.setMaterial(mat_type="refractive", IOR=1.5, dissipation=0.1)
+    assert m.getMaterialBuf() == {"type": 0, "IOR": 1.5, "R": 1.0, "dissipation": 0.1}
+    with pytest.raises(NameError):
+        m.setMaterial(mat_type="glass")
+
+
+def test_light_source_is_seed_reproducible_and_rng_order():
+    np.random.seed(42)
+    a = lsm.light_source(ray_count=100, power=10.0)
+    np.random.seed(42)
+    u = np.random.rand(100, 1)
+    v = np.random.rand(100, 1)
+    el, az = np.arccos(u), 2.0 * np.pi * v
+    assert a.rays_power.shape == (100, 1) and a.rays_dir.dtype == np.float32
+    # direction (0,0,1): elevation0 = 0, azimuth0 = +pi/2; row vector x Rz(pi/2): (x, y, z) -> (y, -x, z)
+    assert np.allclose(a.rays_dir[:, 2], np.cos(el)[:, 0], atol=1e-6)
+    assert np.allclose(a.rays_dir[:, 1], -(np.sin(el) * np.cos(az))[:, 0], atol=1e-6)
+    assert np.allclose(a.rays_dir[:, 0], (np.sin(el) * np.sin(az))[:, 0], atol=1e-6)
+    assert abs(float(a.rays_power.sum()) - 10.0) < 1e-4
+    np.random.seed(42)
+    b = lsm.light_source(ray_count=100, power=10.0)
+    assert np.array_equal(a.rays_dir, b.rays_dir) and np.array_equal(a.rays_power, b.rays_power)
+    b.random_collimated_rays(diameter=2.0)  # consumes two more draws, square footprint, (N,) power
+    assert b.rays_power.shape == (100,) and np.all(np.abs(b.rays_origin[:, :2]) <= 1.0)
+    assert np.allclose(b.rays_dir[:, :3], [0, 0, 1], atol=1e-7)
+
+
+def test_flatten_matches_oracle_flatten():
+    ls, meshes, _ = scenes.human_eye(ray_count=50)
+    o, d, p = it.flatten_light_sources(ls)
+    oo, od, op, oin = oracle.flatten_sources(ls)
+    assert np.array_equal(o, oo) and np.array_equal(d, od) and np.array_equal(p, op)
+    assert it.sorted_sequential_sum_f32(p) == oin
+    flat = it.flatten_meshes(meshes)
+    sc = oracle.Scene(meshes)
+    for k, ref in (("v0", sc.v0), ("v1", sc.v1), ("v2", sc.v2), ("tri_mesh", sc.tri_mesh), ("mat_type", sc.mat_type),
+                   ("ior", sc.ior), ("refl", sc.refl), ("diss", sc.diss)):
+        assert np.array_equal(flat[k], ref), k
+    ls1, _, _ = scenes.nested_cubes(ray_count=7)  # (N,1) power: np.sort along the last axis is a no-op
+    _, _, p1 = it.flatten_light_sources(ls1)
+    seq = np.float32(0)
+    for x in p1.reshape(-1):
+        seq = np.float32(seq + x)
+    assert it.sorted_sequential_sum_f32(p1) == seq
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library must load without a GPU and export exactly what include/*.h declares."""
+    header = open(os.path.join(ROOT, "include", "lightpycl_b200.h")).read()
+    declared = set(re.findall(r"\b(lpcl_[a-z_0-9]+)\s*\(", header))
+    declared -= {"lpcl_step_counters", "lpcl_generation"}
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = _cabi.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.lpcl_abi_version() == _cabi.ABI_VERSION
+    assert ctypes.sizeof(_cabi.StepCounters) == 64 and ctypes.sizeof(_cabi.Generation) == 56
+    # argument errors are reported, not crashed on (no GPU needed: validation happens first)
+    assert lib.lpcl_scene_create(None, None, None, None, None, 0, None, None, None, None, 0, None) == -1
+    assert b"NULL" in lib.lpcl_last_error()
+
+
+def test_tracer_refuses_to_run_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        it.CL_Tracer()
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000003):
+        for ws in (1, 2, 3, 8):
+            b = [dist.shard_bounds(n, ws, r) for r in range(ws)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1

@@ -1,0 +1,196 @@
+"""Seam-level parity on the GPU: each C-ABI entry point with the reference kernels' buffer
+semantics (lpcl_intersect / lpcl_intersect_postproc / lpcl_reflect_refract_rays) is fed the
+exact per-iteration inputs of an oracle trace and must reproduce the oracle's outputs
+bit-for-bit - the same seams as the reference's three launches (iterative_tracer.py:288/303/318)."""
+
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuSeams:
+    def __init__(self, scene):
+        import torch
+
+        from lightpycl_b200 import _cabi
+
+        self.torch, self.lib, self.cabi = torch, _cabi.load(), _cabi
+        self.dev = torch.device("cuda:0")
+        self.M = scene.mesh_count
+        self.v = [torch.from_numpy(a).to(self.dev) for a in (scene.v0, scene.v1, scene.v2)]
+        self.handle = C.c_void_p()
+        rc = self.lib.lpcl_scene_create(C.byref(self.handle), self.v[0].data_ptr(), self.v[1].data_ptr(),
+                                        self.v[2].data_ptr(), scene.tri_mesh.ctypes.data, scene.tri_count,
+                                        scene.mat_type.ctypes.data, scene.ior.ctypes.data, scene.refl.ctypes.data,
+                                        scene.diss.ctypes.data, scene.mesh_count, None)
+        _cabi.check(rc, "lpcl_scene_create")
+
+    def close(self):
+        self.lib.lpcl_scene_destroy(self.handle)
+
+    def t(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+
+    def intersect(self, origin, direc, max_ray_len):
+        torch = self.torch
+        n = len(origin)
+        o, d = self.t(origin), self.t(direc)
+        near_t = torch.empty((n, self.M), dtype=torch.float32, device=self.dev)
+        hits = torch.empty((n, self.M), dtype=torch.int32, device=self.dev)
+        near_tri = torch.empty((n, self.M), dtype=torch.int32, device=self.dev)
+        scratch = torch.empty(self.lib.lpcl_scratch_bytes(self.handle, n), dtype=torch.uint8, device=self.dev)
+        rc = self.lib.lpcl_intersect(self.handle, o.data_ptr(), d.data_ptr(), n, C.c_float(max_ray_len),
+                                     near_t.data_ptr(), hits.data_ptr(), near_tri.data_ptr(), scratch.data_ptr(), None)
+        self.cabi.check(rc, "lpcl_intersect")
+        torch.cuda.synchronize()
+        return near_t.cpu().numpy(), hits.cpu().numpy(), near_tri.cpu().numpy()
+
+    def postproc(self, origin, direc, prev, near_t, hits, near_tri, max_ray_len):
+        torch = self.torch
+        n = len(origin)
+        i32 = lambda: torch.full((n,), -7, dtype=torch.int32, device=self.dev)
+        dest = torch.zeros((n, 4), dtype=torch.float32, device=self.dev)
+        n1, n2, ent, hm, ht = i32(), i32(), torch.zeros(n, dtype=torch.int32, device=self.dev), i32(), i32()
+        args = [self.t(origin), self.t(direc), dest, self.t(prev.astype(np.int32)), n1, n2, ent, hm, ht,
+                self.t(near_t), self.t(hits), self.t(near_tri)]
+        rc = self.lib.lpcl_intersect_postproc(self.handle, *[a.data_ptr() for a in args], n, C.c_float(max_ray_len), None)
+        self.cabi.check(rc, "lpcl_intersect_postproc")
+        torch.cuda.synchronize()
+        return dict(dest=dest.cpu().numpy(), n1=n1.cpu().numpy(), n2=n2.cpu().numpy(), entering=ent.cpu().numpy(),
+                    hit_mesh=hm.cpu().numpy(), hit_tri=ht.cpu().numpy())
+
+    def reflect_refract(self, origin, dest, direc, power, measured, n1, n2, hit_mesh, hit_tri, ior_env):
+        torch = self.torch
+        n = len(origin)
+        f4 = lambda: torch.zeros((n, 4), dtype=torch.float32, device=self.dev)
+        f1 = lambda: torch.zeros(n, dtype=torch.float32, device=self.dev)
+        i1 = lambda: torch.zeros(n, dtype=torch.int32, device=self.dev)
+        pw, ms = self.t(power.reshape(-1)), self.t(measured)
+        out = [f4(), f4(), f1(), i1(), f4(), f4(), f1(), i1()]
+        args = [self.t(origin), self.t(dest), self.t(direc), pw, ms, self.t(n1), self.t(n2)] + out + \
+               [self.t(hit_mesh), self.t(hit_tri)]
+        rc = self.lib.lpcl_reflect_refract_rays(self.handle, *[a.data_ptr() for a in args], n, C.c_float(ior_env), None)
+        self.cabi.check(rc, "lpcl_reflect_refract_rays")
+        torch.cuda.synchronize()
+        keys = ("refl_origin", "refl_dir", "refl_power", "refl_meas", "refr_origin", "refr_dir", "refr_power", "refr_meas")
+        res = {k: v.cpu().numpy() for k, v in zip(keys, out)}
+        res["power"], res["measured"] = pw.cpu().numpy(), ms.cpu().numpy()
+        return res
+
+
+def _cases():
+    from lightpycl_b200 import scenes
+
+    cases = {name: val for name, val in util.mini_scenes().items()}
+    cases["c2_lens_1500"] = scenes.directivity_lens(ray_count=1500)
+    cases["c3_mirror_1500"] = scenes.parabolic_mirror(ray_count=1500)
+    cases["c4_eye_4x150"] = scenes.human_eye(ray_count=150)
+    return cases
+
+
+CASES = None
+
+
+def _get(name):
+    global CASES
+    if CASES is None:
+        CASES = _cases()
+    return CASES[name]
+
+
+NAMES = ["c1_cubes_10", "c1_cubes_300", "mini_lens", "mini_mirror", "mini_lossy", "mini_stack", "c2_lens_1500",
+         "c3_mirror_1500", "c4_eye_4x150"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_three_seams_match_oracle(name):
+    ls, meshes, params = _get(name)
+    ref = oracle.trace(ls, meshes, backend="port", **params)
+    g = GpuSeams(ref["scene"])
+    try:
+        mrl = np.float32(params["max_ray_len"])
+        for k, (res, dbg) in enumerate(zip(ref["results"], ref["debug"])):
+            origin, dest, power_after, meas_after = res
+            direc, prev = dbg["dir"], dbg["prev_mesh"]
+            # 1. search
+            near_t, hits, near_tri = g.intersect(origin, direc, mrl)
+            assert np.array_equal(hits, dbg["hits"]), (name, k, "hits")
+            assert np.array_equal(near_tri, dbg["near_tri"]), (name, k, "near_tri")
+            assert np.array_equal(util.bits(near_t), util.bits(dbg["near_t"])), (name, k, "near_t")
+            # 2. media resolution
+            pp = g.postproc(origin, direc, prev, dbg["near_t"], dbg["hits"], dbg["near_tri"], mrl)
+            for key in ("n1", "n2", "hit_mesh", "hit_tri"):
+                assert np.array_equal(pp[key], dbg[key]), (name, k, key)
+            hit = dbg["hit_mesh"] >= 0
+            assert np.array_equal(pp["entering"][hit], dbg["entering"][hit])
+            assert np.array_equal(util.bits(pp["dest"][:, :3]), util.bits(dest[:, :3])), (name, k, "dest")
+            # 3. Fresnel / materials: feed the parents' PRE-step power and flags
+            if k == 0:
+                p_in = np.ascontiguousarray(oracle.flatten_sources(ls)[2].reshape(-1))
+            else:
+                p_in = p_next
+            m_in = np.zeros(len(origin), np.int32)
+            want = oracle.reflect_refract(ref["scene"], origin, dest, direc, p_in.copy(), m_in.copy(), dbg["n1"],
+                                          dbg["n2"], dbg["hit_mesh"], dbg["hit_tri"], np.float32(params["ior_env"]), mrl)
+            got = g.reflect_refract(origin, dest, direc, p_in.copy(), m_in.copy(), dbg["n1"], dbg["n2"],
+                                    dbg["hit_mesh"], dbg["hit_tri"], np.float32(params["ior_env"]))
+            for key in ("refl_power", "refr_power", "refl_meas", "refr_meas"):
+                assert np.array_equal(util.bits(got[key]), util.bits(want[key])), (name, k, key)
+            for key in ("refl_origin", "refl_dir", "refr_origin", "refr_dir"):
+                assert np.array_equal(util.bits(got[key][:, :3]), util.bits(want[key][:, :3])), (name, k, key)
+            assert np.array_equal(util.bits(got["power"]), util.bits(power_after.reshape(-1))), (name, k, "parent power")
+            assert np.array_equal(got["measured"], meas_after), (name, k, "parent measured")
+            keep = np.concatenate((want["refl_meas"], want["refr_meas"])) == 0
+            p_next = np.ascontiguousarray(np.concatenate((want["refl_power"], want["refr_power"]))[keep])
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("R,chunks", [(1, 1), (2, 1), (4, 1), (1, 7), (2, 3), (4, 64)])
+def test_search_variants_agree(R, chunks):
+    """Rays-per-thread variants and triangle-range splits (atomic merge) give identical results."""
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=5000)
+    sc = oracle.Scene(meshes)
+    origin, direc, _, _ = oracle.flatten_sources(ls)
+    want = oracle.intersect(sc, origin, direc, params["max_ray_len"], "port")
+    g = GpuSeams(sc)
+    os.environ["LPCL_SEARCH_R"], os.environ["LPCL_SEARCH_CHUNKS"] = str(R), str(chunks)
+    try:
+        got = g.intersect(origin, direc, np.float32(params["max_ray_len"]))
+    finally:
+        os.environ.pop("LPCL_SEARCH_R"), os.environ.pop("LPCL_SEARCH_CHUNKS")
+        g.close()
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert np.array_equal(util.bits(got[0]), util.bits(want[0]))
+
+
+def test_error_conventions():
+    from lightpycl_b200 import _cabi, scenes
+
+    import torch
+
+    lib = _cabi.load()
+    _, meshes, _ = scenes.nested_cubes()
+    sc = oracle.Scene(meshes)
+    v = [torch.from_numpy(a).cuda() for a in (sc.v0, sc.v1, sc.v2)]
+    h = C.c_void_p()
+    bad_ids = sc.tri_mesh.copy()
+    bad_ids[bad_ids == 2] = 3  # skips an id -> the reference kernel would silently misbehave (cl:262-265)
+    rc = lib.lpcl_scene_create(C.byref(h), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), bad_ids.ctypes.data,
+                               sc.tri_count, sc.mat_type.ctypes.data, sc.ior.ctypes.data, sc.refl.ctypes.data,
+                               sc.diss.ctypes.data, sc.mesh_count, None)
+    assert rc == -3 and b"mesh" in lib.lpcl_last_error()
+    rc = lib.lpcl_scene_create(C.byref(h), v[0].data_ptr() + 4, v[1].data_ptr(), v[2].data_ptr(),
+                               sc.tri_mesh.ctypes.data, sc.tri_count, sc.mat_type.ctypes.data, sc.ior.ctypes.data,
+                               sc.refl.ctypes.data, sc.diss.ctypes.data, sc.mesh_count, None)
+    assert rc == -4

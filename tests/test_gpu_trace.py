@@ -1,0 +1,135 @@
+"""End-to-end parity of the production path (CL_Tracer -> C ABI -> fused sm_100a kernels) against
+the oracle: `results` bit-identical per iteration (same ray ORDER as the reference), hit
+mesh/triangle/n1/n2 identical, measured (pos, pwr) identical; plus size-independent properties at
+larger ray counts."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _trace_gpu(ls, meshes, params, **kw):
+    from lightpycl_b200 import iterative_tracer as it
+
+    tr = it.CL_Tracer(platform_name="NVIDIA", device_name="B200", record_hits=True, **kw)
+    tr.iterative_tracer(light_source=ls, meshes=meshes, **params)
+    return tr
+
+
+def _check(name, ls, meshes, params, **kw):
+    ref = oracle.trace(ls, meshes, backend="reference" if oracle.available("reference") else "port",
+                       power_sum="f64", **params)
+    tr = _trace_gpu(ls, meshes, params, **kw)
+    util.assert_results_equal(list(tr.results), ref["results"], name)
+    assert tr.results.ray_counts == [len(r[0]) for r in ref["results"]]
+    for k, dbg in enumerate(ref["debug"]):
+        hit = tr.hit_records[k].cpu().numpy()
+        for col, key in enumerate(("hit_mesh", "hit_tri", "n1", "n2")):
+            assert np.array_equal(hit[:, col], dbg[key]), (name, k, key)
+    pos, pwr = tr.get_measured_rays()
+    rpos, rpwr = oracle.measured_rays(ref["results"])
+    if rpwr is not None and np.asarray(rpwr).size:
+        assert np.asarray(pwr).shape == np.asarray(rpwr).shape
+        assert np.array_equal(util.bits(pos[:, :3]), util.bits(rpos[:, :3]))
+        assert np.array_equal(util.bits(np.asarray(pwr)), util.bits(np.asarray(rpwr)))
+        total, rtotal = np.sum(np.asarray(pwr, np.float64)), np.sum(np.asarray(rpwr, np.float64))
+        assert abs(total - rtotal) <= 1e-6 * abs(rtotal)
+        assert abs(sum(tr.stats["measured"]) - np.asarray(rpwr).size) == 0
+    else:
+        assert len(np.asarray(pwr).reshape(-1)) == 0
+    assert tr.stats["live"] == ref["live"]
+    return tr, ref
+
+
+FIXTURES = sorted(glob.glob(os.path.join(util.GOLDEN_DIR, "*.npz")))
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_trace_matches_golden_fixture(path):
+    """GPU against the committed outputs of the reference kernels (same frozen inputs)."""
+    z = np.load(path)
+    ls, meshes = util.arrays_to_scene(z)
+    params = dict(trace_iterations=int(z["param_trace_iterations"]),
+                  trace_until_dissipated=float(z["param_trace_until_dissipated"]),
+                  max_ray_len=np.float32(z["param_max_ray_len"]), ior_env=np.float32(z["param_ior_env"]))
+    tr = _trace_gpu(ls, meshes, params)
+    n_iter = int(z["n_iter"])
+    want = [(z["it%d_origin" % k], z["it%d_dest" % k], z["it%d_power" % k], z["it%d_meas" % k]) for k in range(n_iter)]
+    util.assert_results_equal(list(tr.results), want, os.path.basename(path))
+    for k in range(n_iter):
+        hit = tr.hit_records[k].cpu().numpy()
+        for col, key in enumerate(("hit_mesh", "hit_tri", "n1", "n2")):
+            assert np.array_equal(hit[:, col], z["it%d_%s" % (k, key)]), (k, key)
+    pos, pwr = tr.get_measured_rays()
+    assert np.array_equal(util.bits(pos[:, :3]), util.bits(z["measured_pos"][:, :3]))
+    assert np.array_equal(util.bits(np.asarray(pwr).reshape(-1)), util.bits(z["measured_pwr"]))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("c1_nested_cubes", dict(ray_count=3000)),
+    ("c2_directivity_lens", dict(ray_count=4000)),
+    ("c3_parabolic_mirror", dict(ray_count=3000)),
+    ("c4_human_eye", dict(ray_count=200)),
+    ("dissipative_cube", dict(ray_count=3000)),
+    ("c5_lenslet_array", dict(ray_count=150, sources=4, grid=2, ang_pts=17)),
+    ("c5_lenslet_array", dict(ray_count=100, sources=4, grid=2, ang_pts=9, per_lenslet_mesh=True)),
+])
+def test_trace_matches_oracle_on_configs(name, kw):
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.CONFIGS[name](**kw)
+    _check(name, ls, meshes, params)
+
+
+def test_trace_with_lineage_and_without_results():
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=3000)
+    tr, ref = _check("lens+lineage", ls, meshes, params, lineage=True)
+    # lineage order == reference order: every generation's lineage must be strictly increasing
+    for gen, _dm, _ps in tr.results._dev:
+        lin = gen.logical(gen.lineage).cpu().numpy()
+        assert np.all(np.diff(lin) > 0)
+    lean = _trace_gpu(ls, meshes, params, keep_results=False)
+    a, b = tr.get_measured_rays(), lean.get_measured_rays()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and len(lean.results) == 0
+    assert lean.results.ray_counts == tr.results.ray_counts
+
+
+def test_determinism_and_shard_union_at_scale():
+    """Size-independent properties at 200k rays x 19k triangles (too big for the CPU oracle in a
+    test): (1) two runs are bit-identical; (2) linearity - tracing the two halves of the rays
+    separately yields the same measured records as the full trace (rays are independent);
+    (3) power bookkeeping: measured + live + lost <= input, measured power reproduced by stats."""
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=200_000)
+    a = _trace_gpu(ls, meshes, params, lineage=True)
+    b = _trace_gpu(ls, meshes, params, lineage=True)
+    pa, pb = a.get_measured_rays(), b.get_measured_rays()
+    assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+    assert a.results.ray_counts == b.results.ray_counts
+
+    src = ls[0]
+    halves = []
+    for lo, hi in ((0, 100_000), (100_000, 200_000)):
+        part = util.ArraySource(src.rays_origin[lo:hi], src.rays_dir[lo:hi], src.rays_power[lo:hi])
+        # same number of iterations as the full run so that the same generations are compared
+        p = dict(params, trace_iterations=len(a.results), trace_until_dissipated=1.0)
+        halves.append(_trace_gpu([part], meshes, p).get_measured_rays())
+    full = _trace_gpu(ls, meshes, dict(params, trace_iterations=len(a.results), trace_until_dissipated=1.0))
+    fpos, fpwr = full.get_measured_rays()
+    upos = np.concatenate([h[0] for h in halves])
+    upwr = np.concatenate([np.asarray(h[1]).reshape(-1) for h in halves])
+    key = lambda pos, pwr: np.sort(np.ascontiguousarray(np.concatenate((pos[:, :3], pwr.reshape(-1, 1)), axis=1))
+                                   .view([("", np.float32)] * 4).reshape(-1), axis=0)
+    assert np.array_equal(key(fpos, np.asarray(fpwr).reshape(-1)), key(upos, upwr))
+    measured = float(np.sum(np.asarray(pa[1], np.float64)))
+    assert 0.3 * a.input_power < measured <= a.input_power * (1 + 1e-5)
