@@ -160,9 +160,17 @@ int lpcl_trace_step(const lpcl_scene *scene, const lpcl_generation *parents, con
                     int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
                     void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream);
 
-/* Only the nearest-hit search of lpcl_trace_step (for timing / profiling the dominant kernel). */
+/* The two halves of lpcl_trace_step, callable separately so the caller can put events between
+ * them: lpcl_trace_search runs the nearest-hit search into d_workspace (adds to
+ * d_counters->candidates when d_counters != NULL; does not zero it); lpcl_trace_resolve runs the
+ * fused media-resolution / Fresnel / compaction kernel on that workspace (accumulates into
+ * d_counters, which the caller zeroes).  lpcl_trace_step == zero counters + search + resolve. */
 int lpcl_trace_search(const lpcl_scene *scene, const lpcl_generation *parents, void *d_workspace,
                       float max_ray_len, lpcl_step_counters *d_counters, void *stream);
+int lpcl_trace_resolve(const lpcl_scene *scene, const lpcl_generation *parents, const lpcl_generation *children,
+                       float *d_dest_meas, int32_t *d_hit, float *d_measured_out, uint64_t *d_measured_lineage,
+                       int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
+                       void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream);
 
 /* Pack / unpack helpers between the reference layout and the packed generation layout. */
 int lpcl_pack_rays(const float *d_origin, const float *d_dir, const float *d_power, const int32_t *d_prev_mesh,

@@ -63,6 +63,8 @@ SYMBOLS = {
     "lpcl_step_workspace_bytes": (_i64, [_p, _i64]),
     "lpcl_trace_step": (C.c_int, [_p, C.POINTER(Generation), C.POINTER(Generation), _p, _p, _p, _p, _i64, _i64, _p,
                                   _p, _f, _f, _i32, _p]),
+    "lpcl_trace_resolve": (C.c_int, [_p, C.POINTER(Generation), C.POINTER(Generation), _p, _p, _p, _p, _i64, _i64, _p,
+                                     _p, _f, _f, _i32, _p]),
     "lpcl_trace_search": (C.c_int, [_p, C.POINTER(Generation), _p, _f, _p, _p]),
     "lpcl_pack_rays": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
 }

@@ -33,8 +33,22 @@ static int fail(int code, const char *fmt, ...)
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+typedef void (*SearchFn)(SceneDev, RaysDev, float, unsigned long long *, int *, int, unsigned long long *);
+struct SearchVariant {
+    int R, threads;
+    SearchFn fn;
+};
+// rays per thread x threads per CTA; ordered by rays per CTA
+static const SearchVariant kVariants[] = {
+    {1, 128, search_kernel<1, 128>}, {1, 256, search_kernel<1, 256>}, {2, 256, search_kernel<2, 256>},
+    {4, 128, search_kernel<4, 128>}, {4, 256, search_kernel<4, 256>}, {8, 128, search_kernel<8, 128>},
+};
+static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+static const int kDefaultVariant = 4;
+
 struct lpcl_scene {
     SceneDev dev;
+    int occupancy[8] = {1, 1, 1, 1, 1, 1, 1, 1};
     void *owned = nullptr;      // one allocation: filter tiles | tile table | materials | vmax
     int64_t owned_bytes = 0;
     int sm_count = 148;
@@ -143,9 +157,12 @@ extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const floa
     build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles,
                                                                             (float4 *)(base + off_filter));
     SCENE_TRY(cudaGetLastError());
-    SCENE_TRY(cudaFuncSetAttribute(search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
-    SCENE_TRY(cudaFuncSetAttribute(search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
-    SCENE_TRY(cudaFuncSetAttribute(search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
+    for (int v = 0; v < kNumVariants; ++v) {
+        SCENE_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
+        int occ = 0;
+        SCENE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kVariants[v].fn, kVariants[v].threads, SEARCH_SMEM_BYTES));
+        sc->occupancy[v] = occ > 0 ? occ : 1;
+    }
 #undef SCENE_TRY
     *out = sc;
     return 0;
@@ -180,7 +197,7 @@ extern "C" int64_t lpcl_step_workspace_bytes(const lpcl_scene *s, int64_t n)
     return lpcl_scratch_bytes(s, n) + align_up(step_blocks(n) * 16 + 16, 256) + 256;
 }
 
-// LPCL_SEARCH_R (1, 2 or 4) and LPCL_SEARCH_CHUNKS override the launch heuristics without rebuilding.
+// LPCL_SEARCH_R / LPCL_SEARCH_THREADS / LPCL_SEARCH_CHUNKS override the launch heuristics without rebuilding.
 static int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -198,21 +215,27 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         ((unsigned long long)(*reinterpret_cast<const unsigned *>(&max_ray_len)) << 32) | 0xffffffffull;
     {
         long long blocks = (total + 255) / 256;
-        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        if (blocks > (long long)s->sm_count * 32) blocks = (long long)s->sm_count * 32;
         scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key);
     }
-    // rays per thread: 2 by default, fewer when there are too few rays to give every SM two CTAs
-    int R = env_int("LPCL_SEARCH_R", 0); // 1, 2 or 4 forces the variant (tests / tuning)
-    if (R != 1 && R != 2 && R != 4) {
-        R = 2;
-        while (R > 1 && (n + (int64_t)R * SEARCH_THREADS - 1) / ((int64_t)R * SEARCH_THREADS) < (int64_t)s->sm_count * 2) R >>= 1;
+    // variant: forced by the environment (tests / tuning), else the default, stepping down to fewer
+    // rays per CTA while the last ray block would be mostly padding
+    const int want_r = env_int("LPCL_SEARCH_R", 0), want_t = env_int("LPCL_SEARCH_THREADS", 0);
+    int v = -1;
+    for (int k = 0; k < kNumVariants; ++k)
+        if (kVariants[k].R == want_r && (want_t == 0 || kVariants[k].threads == want_t)) { v = k; break; }
+    if (v < 0) {
+        v = kDefaultVariant;
+        while (v > 0 && n < 16LL * kVariants[v].R * kVariants[v].threads) --v;
     }
-    const int64_t ray_blocks = (n + (int64_t)R * SEARCH_THREADS - 1) / ((int64_t)R * SEARCH_THREADS);
-    // split the triangle range over blockIdx.y until there are ~8 CTAs per SM in flight
-    int64_t chunks = env_int("LPCL_SEARCH_CHUNKS", 0); // > 0 forces the split (tests / tuning)
+    const int64_t per_cta = (int64_t)kVariants[v].R * kVariants[v].threads;
+    const int64_t ray_blocks = (n + per_cta - 1) / per_cta;
+    // split the triangle range over blockIdx.y until the grid is >= 8 full waves: fills the SMs when
+    // rays are few and keeps the partially filled last wave below ~1/8 of the run when they are many
+    int64_t chunks = env_int("LPCL_SEARCH_CHUNKS", 0);
     if (chunks <= 0) {
-        const int64_t want = (int64_t)s->sm_count * 8;
-        chunks = (want + ray_blocks - 1) / ray_blocks;
+        const int64_t wave = (int64_t)s->sm_count * s->occupancy[v];
+        chunks = (8 * wave + ray_blocks - 1) / ray_blocks;
     }
     if (chunks < 1) chunks = 1;
     if (chunks > s->dev.n_tiles) chunks = s->dev.n_tiles;
@@ -220,12 +243,8 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
     int tiles_per_chunk = (int)((s->dev.n_tiles + chunks - 1) / chunks);
     chunks = (s->dev.n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
     dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
-    if (R == 4)
-        search_kernel<4><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
-    else if (R == 2)
-        search_kernel<2><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
-    else
-        search_kernel<1><<<grid, SEARCH_THREADS, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
+    kVariants[v].fn<<<grid, kVariants[v].threads, SEARCH_SMEM_BYTES, stream>>>(s->dev, rays, max_ray_len, key, cnt,
+                                                                              tiles_per_chunk, cand_total);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -344,31 +363,27 @@ extern "C" int lpcl_trace_search(const lpcl_scene *s, const lpcl_generation *par
                          d_counters ? (unsigned long long *)&d_counters->candidates : nullptr, (cudaStream_t)stream_);
 }
 
-extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *parents, const lpcl_generation *children,
-                               float *d_dest_meas, int32_t *d_hit, float *d_measured_out, uint64_t *d_measured_lineage,
-                               int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
-                               void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream_)
+extern "C" int lpcl_trace_resolve(const lpcl_scene *s, const lpcl_generation *parents, const lpcl_generation *children,
+                                  float *d_dest_meas, int32_t *d_hit, float *d_measured_out,
+                                  uint64_t *d_measured_lineage, int64_t measured_base, int64_t measured_capacity,
+                                  lpcl_step_counters *d_counters, void *d_workspace, float max_ray_len, float ior_env,
+                                  int32_t iteration, void *stream_)
 {
-    if (!s || !d_dest_meas || !d_counters || !d_workspace) return fail(LPCL_E_NULL, "lpcl_trace_step: NULL argument");
-    int rc = check_gen(parents, "lpcl_trace_step(parents)", true);
+    if (!s || !d_dest_meas || !d_counters || !d_workspace) return fail(LPCL_E_NULL, "lpcl_trace_resolve: NULL argument");
+    int rc = check_gen(parents, "lpcl_trace_resolve(parents)", true);
     if (rc) return rc;
-    rc = check_gen(children, "lpcl_trace_step(children)", false);
+    rc = check_gen(children, "lpcl_trace_resolve(children)", false);
     if (rc) return rc;
     const int64_t n = parents->n;
-    if (children->capacity < 2 * n) return fail(LPCL_E_RANGE, "lpcl_trace_step: children capacity %lld < 2n = %lld",
+    if (children->capacity < 2 * n) return fail(LPCL_E_RANGE, "lpcl_trace_resolve: children capacity %lld < 2n = %lld",
                                                 (long long)children->capacity, (long long)(2 * n));
     if (d_measured_out && measured_capacity < measured_base + n)
-        return fail(LPCL_E_RANGE, "lpcl_trace_step: measured buffer too small (%lld < %lld)", (long long)measured_capacity,
-                    (long long)(measured_base + n));
+        return fail(LPCL_E_RANGE, "lpcl_trace_resolve: measured buffer too small (%lld < %lld)",
+                    (long long)measured_capacity, (long long)(measured_base + n));
     if (!aligned16(d_dest_meas) || (d_measured_out && !aligned16(d_measured_out)) || (d_hit && !aligned16(d_hit)))
-        return fail(LPCL_E_ALIGN, "lpcl_trace_step: output buffers must be 16-byte aligned");
+        return fail(LPCL_E_ALIGN, "lpcl_trace_resolve: output buffers must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
-
-    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(lpcl_step_counters), stream));
     RaysDev par = to_dev(parents), chi = to_dev(children);
-    rc = launch_search(s, par, max_ray_len, d_workspace, (unsigned long long *)&d_counters->candidates, stream);
-    if (rc) return rc;
-
     char *ws = (char *)d_workspace;
     const unsigned long long *key = (const unsigned long long *)ws;
     const int *cnt = (const int *)(ws + scratch_key_bytes(s, n));
@@ -379,7 +394,22 @@ extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *paren
     unsigned long long *words = (unsigned long long *)(scan + 16);
     step_kernel<<<(unsigned)step_blocks(n), STEP_THREADS, 0, stream>>>(
         s->dev, par, chi, key, cnt, (float4 *)d_dest_meas, (int4 *)d_hit, (float4 *)d_measured_out,
-        (unsigned long long *)d_measured_lineage, measured_base, measured_capacity, (StepCounters *)d_counters, words, ticket, max_ray_len, ior_env, iteration);
+        (unsigned long long *)d_measured_lineage, measured_base, measured_capacity, (StepCounters *)d_counters, words,
+        ticket, max_ray_len, ior_env, iteration);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *parents, const lpcl_generation *children,
+                               float *d_dest_meas, int32_t *d_hit, float *d_measured_out, uint64_t *d_measured_lineage,
+                               int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
+                               void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream_)
+{
+    if (!d_counters) return fail(LPCL_E_NULL, "lpcl_trace_step: NULL counters");
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(lpcl_step_counters), (cudaStream_t)stream_));
+    int rc = lpcl_trace_search(s, parents, d_workspace, max_ray_len, d_counters, stream_);
+    if (rc) return rc;
+    return lpcl_trace_resolve(s, parents, children, d_dest_meas, d_hit, d_measured_out, d_measured_lineage,
+                              measured_base, measured_capacity, d_counters, d_workspace, max_ray_len, ior_env, iteration,
+                              stream_);
 }

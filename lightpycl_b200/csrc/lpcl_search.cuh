@@ -5,17 +5,25 @@
 // Design (B200-first, not a translation of the OpenCL kernel):
 //   * one thread owns R rays whose per-ray constants (D, M = O x D, K) stay in registers for the
 //     whole triangle sweep; rays are read once as coalesced float4;
-//   * triangles are pre-digested once per scene into 64-byte FILTER RECORDS (lpcl_math.cuh) grouped
-//     in tiles of TILE_TRIS that never straddle a mesh; a CTA streams the tiles of its chunk into
-//     shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), STAGES deep, one
-//     elected thread producing, every warp consuming through full/empty mbarriers;
-//   * the per-pair work is a division-free, branch-free FMA filter (19 FMA-pipe + 4 ALU ops) that
-//     every lane of the warp runs on broadcast LDS.128 operands; only the rare candidates (a few
-//     per ray per sweep) take the exact, reference-ordered evaluation that decides the result;
+//   * triangles are pre-digested once per scene into 64-byte FILTER RECORDS (lpcl_math.cuh), stored
+//     PAIR-INTERLEAVED (component k of triangles 2p and 2p+1 adjacent) in tiles of TILE_TRIS that
+//     never straddle a mesh; a CTA streams the tiles of its chunk into shared memory with TMA bulk
+//     copies (cp.async.bulk + mbarrier complete_tx), STAGES deep, one elected thread producing,
+//     every warp consuming through full/empty mbarriers;
+//   * the per-pair work is a division-free, branch-free filter evaluated with PACKED FP32
+//     (fma.rn.f32x2 -> FFMA2: two triangles per instruction, the ray value broadcast as the scalar
+//     .F32 operand).  Measured on B200 (tools/ubench_fp32.cu): a 3-register FFMA issues every 2
+//     cycles (register-bank bandwidth), so the scalar formulation tops out near 55% of the FMA
+//     peak; FFMA2 with the triangle pair held in the operand-reuse cache across the R rays of a
+//     thread reads one even + two odd registers and runs at the full lane rate with half the issue
+//     slots.  19 FMA-pipe lane-ops + 3.5 ALU ops per test;
+//   * only the rare candidates (a few per ray per sweep) take the exact, reference-ordered
+//     evaluation that decides the result;
 //   * per (ray, mesh) results (nearest t + triangle packed into one 64-bit key, crossing count)
 //     are merged with atomicMin / atomicAdd so the triangle range can be split over blockIdx.y
-//     when there are too few rays to fill 148 SMs.  Key order (t bits, triangle index) reproduces
-//     the reference tie rule "first triangle index wins" (cl:278) across chunks.
+//     (used to fill the machine when rays are few and to trim the last-wave tail when they are
+//     many).  Key order (t bits, triangle index) reproduces the reference tie rule "first triangle
+//     index wins" (cl:278) across chunks.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -29,7 +37,6 @@ constexpr int TILE_TRIS = 128;                  // triangles per tile
 constexpr int TILE_F4 = TILE_TRIS * 4;          // float4 per tile
 constexpr int TILE_BYTES = TILE_TRIS * 64;      // 8 KB
 constexpr int STAGES = 4;                       // TMA pipeline depth
-constexpr int SEARCH_THREADS = 256;
 
 struct TileInfo {
     int tri0;   // global index of the tile's first triangle
@@ -139,11 +146,11 @@ __global__ void build_filter_kernel(const float4 *v0, const float4 *v1, const fl
         r.ay = r.az = r.e1x = r.e1y = 0.f;
         r.e1z = r.bx = r.by = r.bz = 0.f;
     }
-    float4 *dst = filter + slot * 4;
-    dst[0] = make_float4(r.nx, r.ny, r.nz, r.g);
-    dst[1] = make_float4(r.e2x, r.e2y, r.e2z, r.ax);
-    dst[2] = make_float4(r.ay, r.az, r.e1x, r.e1y);
-    dst[3] = make_float4(r.e1z, r.bx, r.by, r.bz);
+    // pair-interleaved: component k of triangles (2p, 2p+1) sits at float index p*32 + 2k + (j & 1)
+    float *dst = reinterpret_cast<float *>(filter) + (slot / 2) * 32 + (slot & 1);
+    const float comp[16] = {r.nx, r.ny, r.nz, r.g, r.e2x, r.e2y, r.e2z, r.ax, r.ay, r.az, r.e1x, r.e1y, r.e1z, r.bx, r.by, r.bz};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dst[2 * k] = comp[k];
 }
 
 // ------------------------------------------------------------------------------------------ scratch
@@ -188,9 +195,34 @@ __device__ __noinline__ float exact_candidate(const float4 *tv0, const float4 *t
     return -1.0f;
 }
 
+// ------------------------------------------------------------------------------------------ packed FP32 helpers
+typedef unsigned long long u64;
+// d = a * b + c on two lanes; `a` is a scalar broadcast to both lanes (SASS: FFMA2 Rd, Ra.F32, Rb, Rc)
+__device__ __forceinline__ u64 ffma2_s(float a, u64 b, u64 c)
+{
+    u64 d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%1, %1};\nfma.rn.f32x2 %0, t, %2, %3;\n}" : "=l"(d) : "f"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fmul2_s(float a, u64 b)
+{
+    u64 d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%1, %1};\nmul.rn.f32x2 %0, t, %2;\n}" : "=l"(d) : "f"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
+__device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
+__device__ __forceinline__ u64 pack2(unsigned lo, unsigned hi) { return ((u64)hi << 32) | lo; }
+
 // ------------------------------------------------------------------------------------------ the sweep
-template <int R>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *__restrict__ key,
               int *__restrict__ cnt, int tiles_per_chunk, unsigned long long *cand_total)
 {
@@ -208,7 +240,7 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], SEARCH_THREADS / 32);
+            mbar_init(&empty_bar[s], THREADS / 32);
         }
         mbar_fence_init();
     }
@@ -225,25 +257,23 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
     // per-ray constants
     const float eps = eps_len(max_ray_len);
     const float vmax = *sc.vmax;
-    const long long ray0 = (long long)blockIdx.x * (R * SEARCH_THREADS) + tid;
+    const long long ray0 = (long long)blockIdx.x * (R * THREADS) + tid;
     float dx[R], dy[R], dz[R], mx[R], my[R], mz[R], kk[R], tmin[R];
     int best[R], hits[R];
-    long long ph[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        long long i = ray0 + (long long)r * SEARCH_THREADS;
+        const long long i = ray0 + (long long)r * THREADS;
         if (i < rays.n) {
-            ph[r] = rays.phys(i);
-            float4 o = rays.org_pow[ph[r]], d = rays.dir_prev[ph[r]];
+            const long long ph = rays.phys(i);
+            const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
             dx[r] = d.x; dy[r] = d.y; dz[r] = d.z;
             mx[r] = o.y * d.z - o.z * d.y;
             my[r] = o.z * d.x - o.x * d.z;
             mz[r] = o.x * d.y - o.y * d.x;
             kk[r] = filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax);
         } else {
-            ph[r] = -1;
             dx[r] = dy[r] = dz[r] = mx[r] = my[r] = mz[r] = 0.0f;
-            kk[r] = -1.0f; // negative margin: an absent ray is never a candidate
+            kk[r] = -1.0f; // negative margin: an absent ray is (almost) never a candidate; the exact path re-checks
         }
         tmin[r] = max_ray_len;
         best[r] = -1;
@@ -254,9 +284,9 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
     auto flush = [&](int mesh) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            long long i = ray0 + (long long)r * SEARCH_THREADS;
+            const long long i = ray0 + (long long)r * THREADS;
             if (i < rays.n) {
-                long long slot = (long long)mesh * rays.n + i;
+                const long long slot = (long long)mesh * rays.n + i;
                 if (hits[r]) atomicAdd(&cnt[slot], hits[r]);
                 if (best[r] >= 0) atomicMin(&key[slot], pack_key(tmin[r], best[r]));
             }
@@ -270,56 +300,89 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
     for (int it = 0; it < nt; ++it) {
         const int stage = it % STAGES;
         const int4 ti4 = __ldg(reinterpret_cast<const int4 *>(sc.tiles) + (c0 + it));
-        TileInfo ti;
-        ti.tri0 = ti4.x;
-        ti.count = ti4.y;
-        ti.mesh = ti4.z;
-        if (ti.mesh != cur_mesh) {
+        const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
+        if (mesh != cur_mesh) {
             if (cur_mesh >= 0) flush(cur_mesh);
-            cur_mesh = ti.mesh;
+            cur_mesh = mesh;
         }
         mbar_wait(&full_bar[stage], (unsigned)((it / STAGES) & 1));
-        const float4 *tb = tile_buf + stage * TILE_F4;
+        const ulonglong2 *tb = reinterpret_cast<const ulonglong2 *>(tile_buf + stage * TILE_F4);
+        const int npairs = (count + 1) >> 1;
 
-#pragma unroll 2
-        for (int j = 0; j < ti.count; ++j) {
-            const float4 q0 = tb[j * 4 + 0]; // Nn, G
-            const float4 q1 = tb[j * 4 + 1]; // E2, A.x
-            const float4 q2 = tb[j * 4 + 2]; // A.yz, E1n.xy
-            const float4 q3 = tb[j * 4 + 3]; // E1n.z, B
+#pragma unroll 1
+        for (int p = 0; p < npairs; ++p) {
+            // 8 x LDS.128 (warp-uniform address => broadcast): 16 components x 2 triangles
+            const ulonglong2 l0 = tb[p * 8 + 0], l1 = tb[p * 8 + 1], l2 = tb[p * 8 + 2], l3 = tb[p * 8 + 3];
+            const ulonglong2 l4 = tb[p * 8 + 4], l5 = tb[p * 8 + 5], l6 = tb[p * 8 + 6], l7 = tb[p * 8 + 7];
+            u64 den[R], es[R], un[R], vn[R];
+            // component-major order: the triangle pair is the same operand in R consecutive
+            // FFMA2s, so it is served by the operand-reuse cache
+#pragma unroll
+            for (int r = 0; r < R; ++r) den[r] = fmul2_s(dx[r], l0.x);          // Nn.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) den[r] = ffma2_s(dy[r], l0.y, den[r]);  // Nn.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) den[r] = ffma2_s(dz[r], l1.x, den[r]);  // Nn.z
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float den = dx[r] * q0.x;
-                den = fmaf(dy[r], q0.y, den);
-                den = fmaf(dz[r], q0.z, den);
-                const float e = kk[r] * q0.w;
+                const u64 e = fmul2_s(kk[r], l1.y);                             // eps = K_ray * G_tri
                 // es = eps carrying DEN's sign:  s*x + eps >= 0  <=>  (x + s*eps) has DEN's sign
-                const float es = __uint_as_float((__float_as_uint(den) & 0x80000000u) ^ __float_as_uint(e));
-                float un = fmaf(mx[r], q1.x, es);
-                un = fmaf(my[r], q1.y, un);
-                un = fmaf(mz[r], q1.z, un);
-                un = fmaf(dx[r], q1.w, un);
-                un = fmaf(dy[r], q2.x, un);
-                un = fmaf(dz[r], q2.y, un);
-                float vn = fmaf(mx[r], q2.z, es);
-                vn = fmaf(my[r], q2.w, vn);
-                vn = fmaf(mz[r], q3.x, vn);
-                vn = fmaf(dx[r], q3.y, vn);
-                vn = fmaf(dy[r], q3.z, vn);
-                vn = fmaf(dz[r], q3.w, vn);
-                const float wn = (fmaf(3.0f, es, den) - un) - vn;
-                const unsigned db = __float_as_uint(den);
-                const unsigned bad = ((__float_as_uint(un) ^ db) | (__float_as_uint(vn) ^ db)) | (__float_as_uint(wn) ^ db);
-                if ((int)bad >= 0) { // all three carry DEN's sign: candidate
-                    ++n_cand;
-                    if (ph[r] >= 0) {
-                        const int tri = ti.tri0 + j;
-                        const float t = exact_candidate(sc.v0, sc.v1, sc.v2, rays.org_pow, rays.dir_prev, ph[r], tri, eps);
-                        if (t > 0.0f) {
-                            hits[r] += 1;
-                            if (t < tmin[r]) { // strict: first triangle index wins ties (cl:278)
-                                tmin[r] = t;
-                                best[r] = tri;
+                es[r] = pack2((lo32(den[r]) & 0x80000000u) ^ lo32(e), (hi32(den[r]) & 0x80000000u) ^ hi32(e));
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(mx[r], l2.x, es[r]);    // E2.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(mx[r], l5.x, es[r]);    // E1n.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(my[r], l2.y, un[r]);    // E2.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(my[r], l5.y, vn[r]);    // E1n.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(mz[r], l3.x, un[r]);    // E2.z
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(mz[r], l6.x, vn[r]);    // E1n.z
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(dx[r], l3.y, un[r]);    // A.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(dx[r], l6.y, vn[r]);    // B.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(dy[r], l4.x, un[r]);    // A.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(dy[r], l7.x, vn[r]);    // B.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = ffma2_s(dz[r], l4.y, un[r]);    // A.z
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(dz[r], l7.y, vn[r]);    // B.z
+            unsigned bad_lo[R], bad_hi[R], none = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // wn = (DEN + 3 es) - un - vn   ( = s*|DEN| + s*eps - s*(uN+vN) scaled by s )
+                const u64 wn = fsub2(fsub2(ffma2_s(3.0f, es[r], den[r]), un[r]), vn[r]);
+                bad_lo[r] = ((lo32(un[r]) ^ lo32(den[r])) | (lo32(vn[r]) ^ lo32(den[r]))) | (lo32(wn) ^ lo32(den[r]));
+                bad_hi[r] = ((hi32(un[r]) ^ hi32(den[r])) | (hi32(vn[r]) ^ hi32(den[r]))) | (hi32(wn) ^ hi32(den[r]));
+                none &= bad_lo[r] & bad_hi[r]; // sign bit stays set only if every test failed
+            }
+            if ((int)none >= 0) { // rare: some (ray, triangle) of this pair carries DEN's sign three times
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned bad = h ? bad_hi[r] : bad_lo[r];
+                        if ((int)bad >= 0) {
+                            ++n_cand;
+                            const long long i = ray0 + (long long)r * THREADS;
+                            const int j = 2 * p + h;
+                            if (i < rays.n && j < count) {
+                                const int tri = tri0 + j;
+                                const float t = exact_candidate(sc.v0, sc.v1, sc.v2, rays.org_pow, rays.dir_prev,
+                                                                rays.phys(i), tri, eps);
+                                if (t > 0.0f) {
+                                    hits[r] += 1;
+                                    if (t < tmin[r]) { // strict: first triangle index wins ties (cl:278)
+                                        tmin[r] = t;
+                                        best[r] = tri;
+                                    }
+                                }
                             }
                         }
                     }

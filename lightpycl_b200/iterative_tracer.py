@@ -188,13 +188,16 @@ class CL_Tracer:
                      torch.distributed is initialised).
       shard_input    True: every rank passes the SAME sources and traces its contiguous slice;
                      False: every rank passes its OWN rays (used by bench.py weak scaling).
+      profile        record CUDA events around the search and the resolve kernel of every
+                     generation -> ``self.kernel_times`` (list of dict(rays, search_ms, resolve_ms)).
     """
 
     results = None
     geometry = None
 
     def __init__(self, platform_name="NVIDIA", device_name="770", debug=False, device=None, keep_results=True,
-                 record_hits=False, lineage=None, process_group=None, shard_input=True, verbose=False):
+                 record_hits=False, lineage=None, process_group=None, shard_input=True, verbose=False,
+                 profile=False):
         import torch
 
         self.debug = debug
@@ -216,6 +219,10 @@ class CL_Tracer:
         self.world_size, self.rank = _dist.world(self._group)
         self._lineage = bool(lineage) if lineage is not None else self.world_size > 1
         self.shard_input = shard_input
+        self.profile = profile
+        self.kernel_times = []
+        self.kernel_launches = 0
+        self._job = None
         self._scene = None
         self._scene_tensors = None
         self._workspace = None
@@ -269,13 +276,21 @@ class CL_Tracer:
         power falls below ``(1 - trace_until_dissipated) * input_power`` or no ray is left.
         Returns and stores ``self.results``; also sets ``self.tri_count``, ``self.meshes`` and
         ``self.geometry`` like the reference (it:152-158).
-        """
-        torch = self._torch
-        lib = self._lib
-        t_start = time()
-        max_ray_len = np.float32(max_ray_len)
-        ior_env = np.float32(ior_env)
 
+        Equivalent to ``prepare(light_source, meshes)`` (host flattening, sharding, upload, scene
+        build) followed by ``run(...)`` (the device-resident loop).
+        """
+        t_start = time()
+        self.prepare(light_source, meshes)
+        out = self.run(trace_iterations, trace_until_dissipated, max_ray_len, ior_env)
+        self.timings["iterative_tracer_s"] = time() - t_start
+        return out
+
+    def prepare(self, light_source, meshes):
+        """Host side of it:99-169: flatten sources and meshes to float32 arrays, pick this rank's
+        ray shard, copy rays and geometry to HBM and build the scene handle."""
+        torch = self._torch
+        t0 = time()
         origin, direc, power = flatten_light_sources(light_source)
         flat = flatten_meshes(meshes)
         self.tri_count = np.int32(len(flat["v0"]))
@@ -288,26 +303,52 @@ class CL_Tracer:
 
         # shard the rays over the ranks (contiguous blocks keep the reference order inside a rank)
         n_all = len(origin)
+        input_power = float(sorted_sequential_sum_f32(power))
+        lineage_base = 0
+        pow_shape = None if power.ndim == 1 else power.shape
         if self.world_size > 1 and self.shard_input:
             lo, hi = _dist.shard_bounds(n_all, self.world_size, self.rank)
-            input_power = float(sorted_sequential_sum_f32(power))
-            origin, direc, power_local = origin[lo:hi], direc[lo:hi], power.reshape(n_all, -1)[lo:hi]
-            lineage_base = lo
             pow_shape = None if power.ndim == 1 else (hi - lo,) + power.shape[1:]
-            power = power_local
-        else:
-            input_power = float(sorted_sequential_sum_f32(power))
-            lineage_base = 0
-            pow_shape = None if power.ndim == 1 else power.shape
-            if self.world_size > 1:  # every rank brought its own rays
-                counts = _dist.all_gather_int(len(origin), self._group, self.device)
-                lineage_base = int(sum(counts[: self.rank]))
-                input_power = _dist.all_reduce_sum(input_power, self._group, self.device)
+            origin, direc, power = origin[lo:hi], direc[lo:hi], power.reshape(n_all, -1)[lo:hi]
+            lineage_base = lo
+        elif self.world_size > 1:  # every rank brought its own rays
+            counts = _dist.all_gather_int(len(origin), self._group, self.device)
+            lineage_base = int(sum(counts[: self.rank]))
+            input_power = _dist.all_reduce_sum(input_power, self._group, self.device)
         self.input_power = input_power
+        self.timings["host_flatten_s"] = time() - t0
 
+        t0 = time()
         with torch.cuda.device(self.device):
             self._upload_scene(flat)
             n = len(origin)
+            job = dict(n=n, lineage_base=lineage_base, pow_shape=pow_shape)
+            if n > 0:
+                job["origin"] = torch.from_numpy(np.ascontiguousarray(origin)).to(self.device)
+                job["dir"] = torch.from_numpy(np.ascontiguousarray(direc)).to(self.device)
+                job["power"] = torch.from_numpy(np.ascontiguousarray(power.reshape(-1))).to(self.device)
+            self._job = job
+        self.h2d_bytes = int(sum(flat[k].nbytes for k in ("v0", "v1", "v2")) + n * (16 + 16 + 4))
+        self.timings["upload_s"] = time() - t0
+
+    def run(self, trace_iterations=100, trace_until_dissipated=0.99, max_ray_len=np.float32(1e3),
+            ior_env=np.float32(1.0)):
+        """The device-resident loop (replaces it:241-391).  Can be called repeatedly after one
+        ``prepare``; generation 0 is re-packed from the uploaded source rays every time."""
+        torch = self._torch
+        lib = self._lib
+        t_start = time()
+        max_ray_len = np.float32(max_ray_len)
+        ior_env = np.float32(ior_env)
+        job = self._job
+        input_power = self.input_power
+        pow_shape = job["pow_shape"]
+        prof = self.profile
+        events = []
+
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            n = job["n"]
             results = TraceResults()
             self.results = results
             self.hit_records = []
@@ -315,24 +356,22 @@ class CL_Tracer:
             self._measured_lineage = None
             self._measured_count = 0
             self._measured_per_iter = []
+            self.kernel_launches = 0
             self.stats = dict(rays=[], live=[], power_left=[], candidates=[], measured=[], terminated=[])
             counters_dev = torch.zeros(8, dtype=torch.int64, device=self.device)
             counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
 
             gen = None
             if n > 0:
-                o_d = torch.from_numpy(origin).to(self.device)
-                d_d = torch.from_numpy(direc).to(self.device)
-                p_d = torch.from_numpy(np.ascontiguousarray(power.reshape(-1))).to(self.device)
                 org_pow = torch.empty((n, 4), dtype=torch.float32, device=self.device)
                 dir_prev = torch.empty((n, 4), dtype=torch.float32, device=self.device)
                 lineage = torch.empty(n, dtype=torch.int64, device=self.device) if self._lineage else None
-                rc = lib.lpcl_pack_rays(o_d.data_ptr(), d_d.data_ptr(), p_d.data_ptr(), None, n, lineage_base,
-                                        org_pow.data_ptr(), dir_prev.data_ptr(),
+                rc = lib.lpcl_pack_rays(job["origin"].data_ptr(), job["dir"].data_ptr(), job["power"].data_ptr(), None, n,
+                                        job["lineage_base"], org_pow.data_ptr(), dir_prev.data_ptr(),
                                         lineage.data_ptr() if lineage is not None else None, self._stream())
                 _cabi.check(rc, "lpcl_pack_rays")
+                self.kernel_launches += 1
                 gen = _Generation(org_pow, dir_prev, lineage, n, n, n)
-                del o_d, d_d, p_d
 
             for t_iter in range(int(trace_iterations)):
                 n = gen.n if gen is not None else 0
@@ -352,15 +391,28 @@ class CL_Tracer:
                     self._reserve_measured(self._measured_count + n)
                     ws = self._get_workspace(n)
                     pg, cg = gen.c_struct(), children.c_struct()
-                    rc = lib.lpcl_trace_step(
+                    counters_dev.zero_()
+                    if prof:
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                        ev[0].record(stream)
+                    rc = lib.lpcl_trace_search(self._scene, C.byref(pg), ws.data_ptr(), C.c_float(max_ray_len),
+                                               counters_dev.data_ptr(), self._stream())
+                    _cabi.check(rc, "lpcl_trace_search")
+                    if prof:
+                        ev[1].record(stream)
+                    rc = lib.lpcl_trace_resolve(
                         self._scene, C.byref(pg), C.byref(cg), dest_meas.data_ptr(),
                         hit.data_ptr() if hit is not None else None, self._measured.data_ptr(),
                         self._measured_lineage.data_ptr() if self._measured_lineage is not None else None,
                         self._measured_count, self._measured.shape[0], counters_dev.data_ptr(), ws.data_ptr(),
                         C.c_float(max_ray_len), C.c_float(ior_env), t_iter, self._stream())
-                    _cabi.check(rc, "lpcl_trace_step")
+                    _cabi.check(rc, "lpcl_trace_resolve")
+                    if prof:
+                        ev[2].record(stream)
+                        events.append((n, ev))
+                    self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
                     counters_host.copy_(counters_dev, non_blocking=True)
-                    torch.cuda.current_stream(self.device).synchronize()
+                    stream.synchronize()
                     sc = _cabi.StepCounters.from_buffer_copy(counters_host.numpy().tobytes())
                     c = {k: getattr(sc, k) for k, _ in _cabi.StepCounters._fields_}
                     children.n = c["n_reflect"] + c["n_refract"]
@@ -373,9 +425,13 @@ class CL_Tracer:
                         self.hit_records.append(hit)
                     self._measured_count += c["n_measured"]
                     self._measured_per_iter.append(c["n_measured"])
-                elif self.keep_results:
-                    empty = torch.zeros((0, 4), dtype=torch.float32, device=self.device)
-                    results._append(_Generation(empty, empty, None, 0, 0, 0), empty, pow_shape if t_iter == 0 else None)
+                else:
+                    if self.keep_results:
+                        empty = torch.zeros((0, 4), dtype=torch.float32, device=self.device)
+                        results._append(_Generation(empty, empty, None, 0, 0, 0), empty,
+                                        pow_shape if t_iter == 0 else None)
+                    else:
+                        results.ray_counts.append(0)
                     self._measured_per_iter.append(0)
 
                 # it:372-391, evaluated over ALL ranks
@@ -392,7 +448,11 @@ class CL_Tracer:
                     break
                 if live == 0:
                     break
-        self.timings["iterative_tracer_s"] = time() - t_start
+            if prof:
+                stream.synchronize()
+                self.kernel_times = [dict(rays=n_, search_ms=e[0].elapsed_time(e[1]), resolve_ms=e[1].elapsed_time(e[2]))
+                                     for n_, e in events]
+        self.timings["run_s"] = time() - t_start
         return self.results
 
     def _reserve_measured(self, need):
