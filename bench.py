@@ -323,6 +323,7 @@ def main_native(args):
         "traced_rays_per_s": rays_all / t_max,
         "ray_iterations_per_step": rays_total // args.steps,
         "rays_per_iteration": tr.stats["rays"],
+        "filter_candidates_per_ray": [c / max(r, 1) for c, r in zip(tr.stats["candidates"], tr.stats["rays"])],
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),

@@ -154,7 +154,7 @@ extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const floa
     vmax_kernel<<<(tri_count + 255) / 256, 256, 0, stream>>>(d.v0, d.v1, d.v2, tri_count, vmax_bits);
     vmax_finish_kernel<<<1, 1, 0, stream>>>(vmax_bits, (float *)(base + off_vmax));
     const long long slots = (long long)n_tiles * TILE_TRIS;
-    build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles,
+    build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles, d.vmax,
                                                                             (float4 *)(base + off_filter));
     SCENE_TRY(cudaGetLastError());
     for (int v = 0; v < kNumVariants; ++v) {

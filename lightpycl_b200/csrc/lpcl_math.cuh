@@ -102,24 +102,35 @@ LPCL_HD bool ray_triangle_exact(V3 o, V3 d, V3 a, V3 b, V3 c, float &t)
 //   DEN = (D x E2).E1        = D . Nn            Nn  = E2 x E1
 //   uN  = (D x E2).(O - V0)  = E2 . M + D . A    A   = V0 x E2
 //   vN  = ((O-V0) x E1).D    = E1n . M + D . B   E1n = -E1,  B = E1 x V0
-// (scalar triple-product identities; u = uN/DEN, v = vN/DEN in the reference).  A triangle is a
-// CANDIDATE when, with s = sign(DEN) and eps = K_ray * G_tri,
-//   s*uN >= -eps,  s*vN >= -eps,  s*(uN+vN) <= |DEN| + eps.
-// eps bounds (with a factor > 2 to spare) the sum of the rounding error of this FMA evaluation
-// and of the reference's own float evaluation, including the case where the two disagree on
-// the sign of a tiny DEN:   |err| <= ~60 u |D| Emax (|O| + 2 Vmax),  u = 2^-24,
-// Emax = max(|E1|,|E2|), Vmax = max vertex norm.  We use 128 u.  Every candidate is re-evaluated
-// with ray_triangle_exact, so the filter can only cost time, never change a result; it must
-// merely never reject a triangle the reference accepts.  DEN's 1e-6 cut-off and the t > EPSILON
-// test are left to the exact evaluation.
-struct FilterRec { // 64 bytes, four float4 loads
-    float nx, ny, nz, g;       // Nn, G_tri
+// (scalar triple-product identities; u = uN/DEN, v = vN/DEN in the reference).  The reference
+// accepts only if 0 <= u <= 1 and 0 <= v <= 1 (v <= 1 follows from u + v <= 1), i.e. only if
+// uN (DEN - uN) >= 0 and vN (DEN - vN) >= 0 - two sign-agnostic products, no division, no
+// branch on the sign of DEN.  A triangle is a CANDIDATE when
+//   uN (DEN - uN) + m >= 0   and   vN (DEN - vN) + m >= 0,          m = K2_ray * G2_tri.
+// The parallelogram spanned by the triangle is tested instead of the triangle itself (twice the
+// candidates, still a few per ray per sweep) - that trades three sign tests for two and removes
+// every sign transfer from the inner loop.
+//
+// Margin.  Let eps bound |X_filter - X_reference| for X in {DEN, uN, vN}: the FMA evaluation
+// here carries <= 9 u |D| Emax (|O| + |V0|) and the reference's own float evaluation <= 7 u ...,
+// u = 2^-24, Emax = max(|E1|,|E2|); with L = |O| + 2 Vmax (Vmax = max vertex norm) and a 1.5x
+// allowance take eps = 24 u |D| Emax L.  If the reference accepts (a = uN_ref, d = DEN_ref of
+// equal sign, |a| <= |d|(1+3u)) then a_f (d_f - a_f) >= -(4u d^2 + 3 eps |d| + 2 eps^2) with
+// |d| <= |D| E12, E12 = |E1||E2|, i.e. >= -u |D|^2 Emax L (76 E12 + 1152 u Emax L), which is
+// covered with a factor 2 to spare by the separable product of
+//   K2_ray = 2 u |D|^2 L max(1, L / Lcap),   G2_tri = Emax (76 E12 + 1152 u Emax Lcap),  Lcap = 4 Vmax.
+// Every candidate is re-evaluated with ray_triangle_exact, so the filter can only cost time,
+// never change a result; it must merely never reject a triangle the reference accepts
+// (property-tested on the CPU by tests/test_filter_host.py, and by every parity test).  DEN's
+// 1e-6 cut-off, u + v <= 1 and t > EPSILON are left to the exact evaluation.
+struct FilterRec { // 64 bytes
+    float nx, ny, nz, g;       // Nn, G2_tri
     float e2x, e2y, e2z, ax;   // E2, A.x
     float ay, az, e1x, e1y;    // A.yz, E1n.xy
     float e1z, bx, by, bz;     // E1n.z, B
 };
 
-LPCL_HD FilterRec make_filter_rec(V3 v0, V3 v1, V3 v2)
+LPCL_HD FilterRec make_filter_rec(V3 v0, V3 v1, V3 v2, float vmax)
 {
     V3 e1 = sub(v1, v0), e2 = sub(v2, v0); // float-rounded edges, exactly the reference's E1/E2
     double e1x = e1.x, e1y = e1.y, e1z = e1.z, e2x = e2.x, e2y = e2.y, e2z = e2.z;
@@ -141,17 +152,45 @@ LPCL_HD FilterRec make_filter_rec(V3 v0, V3 v1, V3 v2)
     r.by = (float)(e1z * ox - e1x * oz);
     r.bz = (float)(e1x * oy - e1y * ox);
     double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
-    double g = (l1 > l2 ? l1 : l2) * 1.0001;
+    double emax = l1 > l2 ? l1 : l2;
+    double g = emax * (76.0 * l1 * l2 + 6.9e-5 * emax * 4.0 * (double)vmax) * 1.001; // 1152 * 2^-24 = 6.87e-5
     r.g = (float)(g > 1e-30 ? g : 1e-30);
     return r;
 }
 
-// K_ray = 128 u |D| (|O| + 2 Vmax), rounded up generously
+// K2_ray = 2 u |D|^2 L max(1, L / (4 Vmax)), L = |O| + 2 Vmax, rounded up
 LPCL_HD float filter_ray_scale(V3 o, V3 d, float vmax)
 {
-    float ld = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    float d2 = d.x * d.x + d.y * d.y + d.z * d.z;
     float lo = sqrtf(o.x * o.x + o.y * o.y + o.z * o.z);
-    return 7.7e-6f * ld * (lo + 2.0f * vmax); // 128 * 2^-24 = 7.63e-6
+    float L = lo + 2.0f * vmax;
+    float f = L / (4.0f * vmax);
+    return 1.2e-7f * d2 * L * (f > 1.0f ? f : 1.0f); // 2 * 2^-24 = 1.19e-7
+}
+
+// The filter for one (ray, triangle), operation by operation as the packed device loop evaluates
+// each lane (fma.rn.f32x2 == two fmaf).  Used by the host property test and by nothing on the GPU.
+LPCL_HD bool filter_candidate(const FilterRec &q, float dx, float dy, float dz, float mx, float my, float mz, float k2)
+{
+    float den = dx * q.nx;
+    den = LPCL_FMA(dy, q.ny, den);
+    den = LPCL_FMA(dz, q.nz, den);
+    float un = mx * q.e2x;
+    un = LPCL_FMA(my, q.e2y, un);
+    un = LPCL_FMA(mz, q.e2z, un);
+    un = LPCL_FMA(dx, q.ax, un);
+    un = LPCL_FMA(dy, q.ay, un);
+    un = LPCL_FMA(dz, q.az, un);
+    float vn = mx * q.e1x;
+    vn = LPCL_FMA(my, q.e1y, vn);
+    vn = LPCL_FMA(mz, q.e1z, vn);
+    vn = LPCL_FMA(dx, q.bx, vn);
+    vn = LPCL_FMA(dy, q.by, vn);
+    vn = LPCL_FMA(dz, q.bz, vn);
+    const float m = k2 * q.g;
+    const float pu = LPCL_FMA(un, LPCL_SUB(den, un), m);
+    const float pv = LPCL_FMA(vn, LPCL_SUB(den, vn), m);
+    return !(signbit(pu) || signbit(pv));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,7 +16,8 @@
 //     cycles (register-bank bandwidth), so the scalar formulation tops out near 55% of the FMA
 //     peak; FFMA2 with the triangle pair held in the operand-reuse cache across the R rays of a
 //     thread reads one even + two odd registers and runs at the full lane rate with half the issue
-//     slots.  19 FMA-pipe lane-ops + 3.5 ALU ops per test;
+//     slots.  The filter is two sign-agnostic products (lpcl_math.cuh): 20 FMA-pipe lane-ops
+//     + 1.5 ALU ops per test;
 //   * only the rare candidates (a few per ray per sweep) take the exact, reference-ordered
 //     evaluation that decides the result;
 //   * per (ray, mesh) results (nearest t + triangle packed into one 64-bit key, crossing count)
@@ -130,7 +131,7 @@ __global__ void vmax_finish_kernel(const unsigned *vmax2_bits, float *vmax)
 }
 
 __global__ void build_filter_kernel(const float4 *v0, const float4 *v1, const float4 *v2, const TileInfo *tiles,
-                                    int n_tiles, float4 *filter)
+                                    int n_tiles, const float *vmax, float4 *filter)
 {
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= (long long)n_tiles * TILE_TRIS) return;
@@ -139,7 +140,7 @@ __global__ void build_filter_kernel(const float4 *v0, const float4 *v1, const fl
     FilterRec r;
     if (j < ti.count) {
         float4 a = v0[ti.tri0 + j], b = v1[ti.tri0 + j], c = v2[ti.tri0 + j];
-        r = make_filter_rec(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z));
+        r = make_filter_rec(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), *vmax);
     } else { // padding: never swept (loops stop at ti.count); negative margin makes it inert anyway
         r.nx = r.ny = r.nz = 0.f; r.g = -1.f;
         r.e2x = r.e2y = r.e2z = r.ax = 0.f;
@@ -208,6 +209,12 @@ __device__ __forceinline__ u64 fmul2_s(float a, u64 b)
 {
     u64 d;
     asm("{\n.reg .b64 t;\nmov.b64 t, {%1, %1};\nmul.rn.f32x2 %0, t, %2;\n}" : "=l"(d) : "f"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
 __device__ __forceinline__ u64 fsub2(u64 a, u64 b)
@@ -314,29 +321,23 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
             // 8 x LDS.128 (warp-uniform address => broadcast): 16 components x 2 triangles
             const ulonglong2 l0 = tb[p * 8 + 0], l1 = tb[p * 8 + 1], l2 = tb[p * 8 + 2], l3 = tb[p * 8 + 3];
             const ulonglong2 l4 = tb[p * 8 + 4], l5 = tb[p * 8 + 5], l6 = tb[p * 8 + 6], l7 = tb[p * 8 + 7];
-            u64 den[R], es[R], un[R], vn[R];
+            u64 den[R], un[R], vn[R];
             // component-major order: the triangle pair is the same operand in R consecutive
             // FFMA2s, so it is served by the operand-reuse cache
 #pragma unroll
             for (int r = 0; r < R; ++r) den[r] = fmul2_s(dx[r], l0.x);          // Nn.x
 #pragma unroll
+            for (int r = 0; r < R; ++r) un[r] = fmul2_s(mx[r], l2.x);           // E2.x
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = fmul2_s(mx[r], l5.x);           // E1n.x
+#pragma unroll
             for (int r = 0; r < R; ++r) den[r] = ffma2_s(dy[r], l0.y, den[r]);  // Nn.y
-#pragma unroll
-            for (int r = 0; r < R; ++r) den[r] = ffma2_s(dz[r], l1.x, den[r]);  // Nn.z
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const u64 e = fmul2_s(kk[r], l1.y);                             // eps = K_ray * G_tri
-                // es = eps carrying DEN's sign:  s*x + eps >= 0  <=>  (x + s*eps) has DEN's sign
-                es[r] = pack2((lo32(den[r]) & 0x80000000u) ^ lo32(e), (hi32(den[r]) & 0x80000000u) ^ hi32(e));
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) un[r] = ffma2_s(mx[r], l2.x, es[r]);    // E2.x
-#pragma unroll
-            for (int r = 0; r < R; ++r) vn[r] = ffma2_s(mx[r], l5.x, es[r]);    // E1n.x
 #pragma unroll
             for (int r = 0; r < R; ++r) un[r] = ffma2_s(my[r], l2.y, un[r]);    // E2.y
 #pragma unroll
             for (int r = 0; r < R; ++r) vn[r] = ffma2_s(my[r], l5.y, vn[r]);    // E1n.y
+#pragma unroll
+            for (int r = 0; r < R; ++r) den[r] = ffma2_s(dz[r], l1.x, den[r]);  // Nn.z
 #pragma unroll
             for (int r = 0; r < R; ++r) un[r] = ffma2_s(mz[r], l3.x, un[r]);    // E2.z
 #pragma unroll
@@ -356,13 +357,14 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
             unsigned bad_lo[R], bad_hi[R], none = 0xffffffffu;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                // wn = (DEN + 3 es) - un - vn   ( = s*|DEN| + s*eps - s*(uN+vN) scaled by s )
-                const u64 wn = fsub2(fsub2(ffma2_s(3.0f, es[r], den[r]), un[r]), vn[r]);
-                bad_lo[r] = ((lo32(un[r]) ^ lo32(den[r])) | (lo32(vn[r]) ^ lo32(den[r]))) | (lo32(wn) ^ lo32(den[r]));
-                bad_hi[r] = ((hi32(un[r]) ^ hi32(den[r])) | (hi32(vn[r]) ^ hi32(den[r]))) | (hi32(wn) ^ hi32(den[r]));
-                none &= bad_lo[r] & bad_hi[r]; // sign bit stays set only if every test failed
+                const u64 m = fmul2_s(kk[r], l1.y);                             // margin = K2_ray * G2_tri
+                const u64 pu = ffma2(un[r], fsub2(den[r], un[r]), m);           // uN (DEN - uN) + m
+                const u64 pv = ffma2(vn[r], fsub2(den[r], vn[r]), m);           // vN (DEN - vN) + m
+                bad_lo[r] = lo32(pu) | lo32(pv);                                // sign bit set => rejected
+                bad_hi[r] = hi32(pu) | hi32(pv);
+                none &= bad_lo[r] & bad_hi[r]; // sign bit stays set only if every test of the pair failed
             }
-            if ((int)none >= 0) { // rare: some (ray, triangle) of this pair carries DEN's sign three times
+            if ((int)none >= 0) { // rare: some (ray, triangle) of this pair passed both product tests
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
 #pragma unroll
