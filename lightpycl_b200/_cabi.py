@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblightpycl_b200.so")
+# LPCL_LIB points at an alternative build of the same ABI (kernel experiments); default: in-tree
+LIB_PATH = os.environ.get("LPCL_LIB") or os.path.join(_HERE, "_lib", "liblightpycl_b200.so")
 
 ABI_VERSION = 1
 
