@@ -150,6 +150,7 @@ def cpu_reference_run(name, cpu_rays, steps, warmup):
     else:
         oracle.build()
         backend, kind = "port_fast", "port"
+    cores = oracle.set_threads(backend)  # all host threads (torchrun exports OMP_NUM_THREADS=1)
     ls, meshes, params = build_workload(name, cpu_rays)
     tri = None
     times, tests, rays = [], 0, 0
@@ -164,7 +165,6 @@ def cpu_reference_run(name, cpu_rays, steps, warmup):
             tests = rays * tri
     total = sum(times)
     value = tests * len(times) / total
-    cores = os.cpu_count()
     sample = "%d source rays x %d triangles, full trace (%d ray-iterations/step), %s via g++ -O3/OpenMP" % (
         cpu_rays, tri, rays, "reference .cl" if kind == "reference" else "C restatement")
     return dict(value=value, rays_per_s=rays * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
@@ -205,6 +205,7 @@ def main_native(args):
         import torch.distributed as td
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
         torch.cuda.set_device(local_rank)
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
@@ -312,6 +313,16 @@ def main_native(args):
     sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # TFLOP/s: SMs x 128 lanes x 2 x f_SM
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dram bytes per launch from the committed `ncu --set full` capture of this same workload
+    traffic = {"search_kernel": None, "step_kernel": None}
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        for k in traffic:
+            v = cap["kernels"].get(k, [{}])[0]
+            tot = v.get("dram_read_bytes", float("nan")) + v.get("dram_write_bytes", float("nan"))
+            traffic[k] = tot if tot == tot else None  # NaN -> null
+    except Exception:
+        pass
     search_tflops = FLOP_PER_TEST * (rays_total * tri) / (search_ms * 1e-3) / 1e12 if search_ms else 0.0
     resolve_gbs = resolve_bytes / (resolve_ms * 1e-3) / 1e9 if resolve_ms else 0.0
 
@@ -329,7 +340,9 @@ def main_native(args):
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": "lpcl::search_kernel", "bound": "fp32", "achieved": search_tflops, "peak": fp32_peak,
-            "unit": "TFLOP/s", "frac": search_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": search_tflops / fp32_peak if fp32_peak else None,
+            "traffic": traffic["search_kernel"], "traffic_note": "dram read+write bytes per launch, ncu --set full "
+            "(profiles/r1_ncu_traffic.json); algorithmic DRAM bytes per launch = 32 B/ray + 64 B/triangle",
             "peak_source": "SMs x 128 FP32 lanes x 2 x sm_max_mhz (%d x 128 x 2 x %.0f MHz); the search is "
                            "FMA-pipe bound, neither HBM nor tensor (SURVEY.md 8(d)); MEASURED_PEAKS.json has no "
                            "FP32 entry" % (sm_count, sm_max_mhz),
@@ -340,7 +353,7 @@ def main_native(args):
         },
         "roofline_material": {
             "kernel": "lpcl::step_kernel", "bound": "hbm", "achieved": resolve_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": resolve_gbs / hbm_peak if hbm_peak else None, "traffic": None,
+            "frac": resolve_gbs / hbm_peak if hbm_peak else None, "traffic": traffic["step_kernel"],
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "algorithmic_bytes": "132 B per parent + 44 B per surviving child (SURVEY.md 8(d))",
             "avg_launch_ms": resolve_ms / max(n_search, 1), "share_of_step": resolve_ms / sum(step_ms) if step_ms else None,

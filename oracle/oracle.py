@@ -68,6 +68,14 @@ def _lib(backend):
     return _loaded[backend]
 
 
+def set_threads(backend, n=None):
+    """Use n (default: all) host threads in the OpenMP loops of `backend`; returns the count in use."""
+    lib = _lib(backend)
+    pre = "ref" if backend.startswith("reference") else "orc"
+    getattr(lib, pre + "_set_threads")(C.c_int(int(n or os.cpu_count() or 1)))
+    return int(getattr(lib, pre + "_max_threads")())
+
+
 def _f(a):
     assert a.dtype == np.float32 and a.flags.c_contiguous
     return a.ctypes.data_as(_fp)

@@ -92,6 +92,16 @@ int ref_intersect_triangle(const float *O, const float *D, const float *V0, cons
                               float3(V1[0], V1[1], V1[2]), float3(V2[0], V2[1], V2[2]), t, u, v);
 }
 
+/* thread control for the timing build (torchrun exports OMP_NUM_THREADS=1) */
+#ifdef _OPENMP
+#include <omp.h>
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ref_max_threads(void) { return omp_get_max_threads(); }
+#else
+void ref_set_threads(int n) { (void)n; }
+int ref_max_threads(void) { return 1; }
+#endif
+
 int ref_build_flags(void)
 {
 #ifdef LPCL_REF_FAST

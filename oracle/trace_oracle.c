@@ -375,3 +375,13 @@ void orc_reflect_refract(int n, const float *origin, const float *dest, const fl
 }
 
 int orc_abi_version(void) { return 1; }
+
+/* thread control for the timing builds (torchrun exports OMP_NUM_THREADS=1) */
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_max_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_max_threads(void) { return 1; }
+#endif
