@@ -177,6 +177,24 @@ int lpcl_pack_rays(const float *d_origin, const float *d_dir, const float *d_pow
                    int64_t n, int64_t lineage_base, float *d_org_pow, float *d_dir_prev, uint64_t *d_lineage,
                    void *stream);
 
+/* ---------------------------------------------------------------- measured-ray post-processing
+ * (the consumer of the measured buffer; O(K), once per run.)
+ *
+ * lpcl_project: the reference kernels `stereograph_project` (.cl:488, launched it:515; kind = 1) and
+ * `angular_project` (.cl:509, launched it:546,602; kind = 2), or the plain (x, y, power) that
+ * get_binned_data bins (it:413-418; kind = 0).  d_records: (k,4) f32 (x, y, z, power) as written
+ * by lpcl_trace_resolve; h_rot9: row-major 3x3 rotation (reference R_dev rows 0..2), NULL = identity;
+ * outputs d_x, d_y, d_pwr_cor: (k,) f32 like the kernels' x / y / pwrs_cor buffers.
+ *
+ * lpcl_bin2d: np.histogram2d(x, y, bins=points, range=limits, weights=float64(w)/denom) as called at
+ * it:416,529,560.  d_xedges, d_yedges: (points+1,) f64 bin edges (np.linspace(lo, hi, points+1));
+ * d_hist: (points, points) f64, zeroed by the call, H[x_bin][y_bin]; right-most edge inclusive.
+ */
+int lpcl_project(const float *d_records, int64_t k, const float *h_rot9, int32_t kind, float *d_x, float *d_y,
+                 float *d_pwr_cor, void *stream);
+int lpcl_bin2d(const float *d_x, const float *d_y, const float *d_w, int64_t k, const double *d_xedges,
+               const double *d_yedges, int32_t points, double denom, double *d_hist, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

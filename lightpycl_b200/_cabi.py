@@ -68,6 +68,8 @@ SYMBOLS = {
                                      _p, _f, _f, _i32, _p]),
     "lpcl_trace_search": (C.c_int, [_p, C.POINTER(Generation), _p, _f, _p, _p]),
     "lpcl_pack_rays": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
+    "lpcl_project": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _p, _p]),
+    "lpcl_bin2d": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i32, C.c_double, _p, _p]),
 }
 
 _lib = None

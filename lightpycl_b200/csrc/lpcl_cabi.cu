@@ -413,3 +413,36 @@ extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *paren
                               measured_base, measured_capacity, d_counters, d_workspace, max_ray_len, ior_env, iteration,
                               stream_);
 }
+
+// ------------------------------------------------------------------------------------------ post-processing
+#include "lpcl_project.cuh"
+
+extern "C" int lpcl_project(const float *d_records, int64_t k, const float *h_rot9, int32_t kind, float *d_x, float *d_y,
+                            float *d_pwr_cor, void *stream_)
+{
+    if (!d_records || !d_x || !d_y || !d_pwr_cor) return fail(LPCL_E_NULL, "lpcl_project: NULL argument");
+    if (k <= 0) return fail(LPCL_E_RANGE, "lpcl_project: k must be > 0");
+    if (kind < 0 || kind > 2) return fail(LPCL_E_RANGE, "lpcl_project: kind must be 0 (xy), 1 (stereographic) or 2 (angular)");
+    if (!aligned16(d_records)) return fail(LPCL_E_ALIGN, "lpcl_project: records must be 16-byte aligned");
+    Rot3 rot;
+    for (int i = 0; i < 9; ++i) rot.r[i] = h_rot9 ? h_rot9[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
+    project_kernel<<<(unsigned)((k + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const float4 *)d_records, k, rot, kind,
+                                                                                 d_x, d_y, d_pwr_cor);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpcl_bin2d(const float *d_x, const float *d_y, const float *d_w, int64_t k, const double *d_xedges,
+                          const double *d_yedges, int32_t points, double denom, double *d_hist, void *stream_)
+{
+    if (!d_x || !d_y || !d_w || !d_xedges || !d_yedges || !d_hist) return fail(LPCL_E_NULL, "lpcl_bin2d: NULL argument");
+    if (k < 0 || points <= 0) return fail(LPCL_E_RANGE, "lpcl_bin2d: k >= 0 and points > 0 required");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(double) * (size_t)points * points, stream));
+    if (k > 0) {
+        bin2d_kernel<<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(d_x, d_y, d_w, k, d_xedges, d_yedges, points, denom,
+                                                                     d_hist);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}

@@ -77,6 +77,16 @@ def all_reduce_sum(value, group, device):
     return float(t.item())
 
 
+def all_reduce_array(arr, group, device):
+    """all-reduce(sum) of a NumPy float64 array (the per-rank histograms of the binning step)."""
+    import numpy as np
+
+    td = _td()
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(_comm_device(group, device))
+    td.all_reduce(t, op=td.ReduceOp.SUM, group=_pg(group))
+    return t.cpu().numpy()
+
+
 def all_reduce_pair(live, power, group, device):
     """One all-reduce(sum) of {live ray count, live power} (counts are exact in float64 < 2^53)."""
     td = _td()

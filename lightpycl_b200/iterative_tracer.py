@@ -498,38 +498,100 @@ class CL_Tracer:
             return torch.zeros((0, 4), dtype=torch.float32, device=self.device)
         return self._measured[: self._measured_count]
 
-    def get_binned_data(self, limits=((-10, 10), (-10, 10)), points=500):
-        """it:413-418: 2-D histogram of measured end points (x, y) weighted by power."""
-        (pos, pwr) = self.get_measured_rays()
-        (H, x_coord, y_coord) = np.histogram2d(x=pos[:, 0], y=pos[:, 1], bins=points, range=limits,
-                                               weights=np.asarray(pwr).reshape(-1))
-        self.hist_data = (H, x_coord, y_coord)
-        return self.hist_data
-
-    def _projected(self, kind, rot=None):
+    def _binned(self, kind, limits, points, rot=None):
+        """Projection + weighted 2-D histogram on the GPU (csrc/lpcl_project.cuh): the measured-ray
+        buffer stays in HBM, only the (points x points) float64 histogram is downloaded.  With
+        world_size > 1 every rank bins its own records and the histograms are all-reduced."""
         from . import projection
 
-        (pos, pwr) = self.get_measured_rays()
-        return projection.project(kind, pos, np.asarray(pwr).reshape(-1), rot)
+        H, xe, ye = projection.project_bin_device(self._lib, self.measured_device(), kind, limits, int(points), rot)
+        if self.world_size > 1:
+            H = _dist.all_reduce_array(H, self._group, self.device)
+        self.hist_data = (H, xe, ye)
+        return self.hist_data
+
+    def get_binned_data(self, limits=((-10, 10), (-10, 10)), points=500):
+        """it:413-418: 2-D histogram of measured end points (x, y) weighted by power."""
+        return self._binned("xy", limits, points)
 
     def get_binned_data_stereographic(self, limits=((-1, 1), (-1, 1)), points=500):
-        """it:503-531."""
-        x, y, pwr = self._projected("stereographic")
-        return self._bin(x, y, pwr, limits, points)
+        """it:503-531: stereographic projection (cl:488-506) + binning, weights / (dx dy)."""
+        return self._binned("stereographic", limits, points)
 
     def get_binned_data_angular(self, limits=((-1, 1), (-1, 1)), points=500):
-        """it:534-562."""
-        x, y, pwr = self._projected("angular")
-        return self._bin(x, y, pwr, limits, points)
+        """it:534-562: azimuth/elevation map (cl:509-538) + binning, weights / (dx dy)."""
+        return self._binned("angular", limits, points)
 
-    def _bin(self, x, y, pwr, limits, points):
-        dx = np.float64(limits[0][1] - limits[0][0]) / np.float64(points)
-        dy = np.float64(limits[1][1] - limits[1][0]) / np.float64(points)
-        w = np.float64(pwr) / (dx * dy)  # it:553-558
-        (H, x_coord, y_coord) = np.histogram2d(x=x.flatten(), y=y.flatten(), bins=points, range=limits,
-                                               weights=w.flatten())
-        self.hist_data = (H, x_coord, y_coord)
+    def get_binned_data_replicated(self, limits=((-10, 10), (-10, 10)), points=500, axis="z", sources=36):
+        """Data part of replicate_lightsources_and_plot (it:564-628): emulate ``sources`` light
+        sources by rotating the measured rays about the symmetry ``axis`` in steps of 2 pi / sources
+        (angular projection per step) and summing the histograms."""
+        from . import light_source as _ls
+
+        R = {"x": _ls._Rx, "X": _ls._Rx, "y": _ls._Ry, "Y": _ls._Ry, "z": _ls._Rz, "Z": _ls._Rz}.get(axis, _ls._Rx)
+        total = None
+        for k in range(int(sources)):
+            H, xe, ye = self._binned("angular", limits, points, rot=R(k * 2.0 * np.pi / sources).astype(np.float32))
+            total = H if total is None else total + H
+        self.hist_data = (total, xe, ye)
         return self.hist_data
+
+    # ---------------------------------------------------------------------------------- beam metrics
+    def _elevations(self, pole):
+        (pos, pwr) = self.get_measured_rays()
+        p = np.asarray(pos, dtype=np.float32)
+        pos0 = p / np.linalg.norm(p, axis=1)[:, None]  # it:424,447,472
+        return np.arccos(np.dot(pos0, np.asarray(pole))), np.float64(np.asarray(pwr).reshape(-1))
+
+    def get_elevation_histogram(self, points=500, pole=[0, 0, 1, 0]):
+        """Data part of plot_elevation_histogram (it:420-441): power per elevation bin divided by
+        sin(elevation) * d_elevation.  Returns (elevation bin centres [rad], intensity)."""
+        elevation, pwr = self._elevations(pole)
+        (H, x) = np.histogram(elevation, bins=points, weights=pwr)
+        x = (x[0:-1] + x[1:]) / 2.0
+        dx = x[1] - x[0]
+        return x, H / (np.sin(x) * dx)
+
+    def get_beam_width_half_power(self, points=500, pole=[0, 0, 1, 0]):
+        """it:443-466: elevation inside which half of the measured power falls.  Prints the
+        reference's three lines and returns (total power, half-power angle [rad], throughput)."""
+        elevation0, pwr0 = self._elevations(pole)
+        order = np.argsort(elevation0, kind="stable")
+        elevation, pwr = elevation0[order], pwr0[order]
+        pwr_cumsum = np.cumsum(pwr)
+        pwr_hmax = pwr_cumsum[-1] / 2.0
+        dev = np.absolute(pwr_cumsum - pwr_hmax)
+        idx = np.where(dev == dev.min())
+        elevation_hmax, pwr_sum_hmax = elevation[idx], pwr_cumsum[idx]
+        print("")
+        print("Throughput results:")
+        print("===================")
+        print("Total measured power: ", pwr_cumsum[-1])
+        print("Beam halfpower angle: ", elevation_hmax / np.pi * 180.0, "Deg")
+        print("Halfwidth throughput: ", pwr_sum_hmax / pwr_cumsum[-1] * 100.0, "%")
+        return pwr_cumsum[-1], elevation_hmax, pwr_sum_hmax / pwr_cumsum[-1]
+
+    def get_beam_HWHM(self, points=500, pole=[0, 0, 1, 0]):
+        """it:468-501: half width at half maximum of the elevation intensity histogram.  Prints the
+        reference's three lines and returns (total power, HWHM angle [rad], throughput)."""
+        elevation0, pwr0 = self._elevations(pole)
+        order = np.argsort(elevation0, kind="stable")
+        (H, x) = np.histogram(a=elevation0[order], bins=points, weights=pwr0[order])
+        x = (x[0:-1] + x[1:]) / 2.0
+        H = (H.T / np.sin(x)).flatten()
+        pwr_hmax = max(H) / 2.0
+        dev = np.absolute(H - pwr_hmax)
+        idx = np.where(dev == dev.min())[0]
+        elevation_hmax = x[idx]
+        total = pwr0.sum()
+        pwr_sum_hmax = np.sum(pwr0[np.where(elevation0 < elevation_hmax[0])]) if len(elevation_hmax) else 0.0
+        print("")
+        print("Throughput results HWHM:")
+        print("========================")
+        print("Total measured power: ", total)
+        print("Beam HWHM angle:      ", elevation_hmax / np.pi * 180.0, "Deg")
+        print("HWHM throughput:      ", pwr_sum_hmax / total * 100.0, "%")
+        return total, elevation_hmax, pwr_sum_hmax / total
 
     # ---------------------------------------------------------------------------------- persistence
     def pickle_results(self):
