@@ -223,6 +223,13 @@ __device__ __forceinline__ u64 fsub2(u64 a, u64 b)
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// (a | b) & c as ONE LOP3 (opaque to the optimiser, which would otherwise materialise a | b)
+__device__ __forceinline__ unsigned or_and(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xA8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
 __device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
 __device__ __forceinline__ u64 pack2(unsigned lo, unsigned hi) { return ((u64)hi << 32) | lo; }
@@ -265,23 +272,20 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
     const float eps = eps_len(max_ray_len);
     const float vmax = *sc.vmax;
     const long long ray0 = (long long)blockIdx.x * (R * THREADS) + tid;
-    float dx[R], dy[R], dz[R], mx[R], my[R], mz[R], kk[R], tmin[R];
+    float dx[R], dy[R], dz[R], mx[R], my[R], mz[R], tmin[R];
     int best[R], hits[R];
+    float kmax = 0.0f; // margin scale K2 shared by the thread's R rays (their maximum): one FMUL2 per pair
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long i = ray0 + (long long)r * THREADS;
-        if (i < rays.n) {
-            const long long ph = rays.phys(i);
-            const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
-            dx[r] = d.x; dy[r] = d.y; dz[r] = d.z;
-            mx[r] = o.y * d.z - o.z * d.y;
-            my[r] = o.z * d.x - o.x * d.z;
-            mz[r] = o.x * d.y - o.y * d.x;
-            kk[r] = filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax);
-        } else {
-            dx[r] = dy[r] = dz[r] = mx[r] = my[r] = mz[r] = 0.0f;
-            kk[r] = -1.0f; // negative margin: an absent ray is (almost) never a candidate; the exact path re-checks
-        }
+        // a lane beyond the last ray sweeps a copy of the last ray (same cost, never flushed)
+        const long long i = min(ray0 + (long long)r * THREADS, rays.n - 1);
+        const long long ph = rays.phys(i);
+        const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
+        dx[r] = d.x; dy[r] = d.y; dz[r] = d.z;
+        mx[r] = o.y * d.z - o.z * d.y;
+        my[r] = o.z * d.x - o.x * d.z;
+        mz[r] = o.x * d.y - o.y * d.x;
+        kmax = fmaxf(kmax, filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax));
         tmin[r] = max_ray_len;
         best[r] = -1;
         hits[r] = 0;
@@ -354,23 +358,24 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
             for (int r = 0; r < R; ++r) un[r] = ffma2_s(dz[r], l4.y, un[r]);    // A.z
 #pragma unroll
             for (int r = 0; r < R; ++r) vn[r] = ffma2_s(dz[r], l7.y, vn[r]);    // B.z
-            unsigned bad_lo[R], bad_hi[R], none = 0xffffffffu;
+            const u64 m = fmul2_s(kmax, l1.y);                                  // margin = K2 * G2_tri
+            u64 pu[R], pv[R];
+            unsigned none = 0xffffffffu; // sign bit stays set only if every test of the pair failed
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const u64 m = fmul2_s(kk[r], l1.y);                             // margin = K2_ray * G2_tri
-                const u64 pu = ffma2(un[r], fsub2(den[r], un[r]), m);           // uN (DEN - uN) + m
-                const u64 pv = ffma2(vn[r], fsub2(den[r], vn[r]), m);           // vN (DEN - vN) + m
-                bad_lo[r] = lo32(pu) | lo32(pv);                                // sign bit set => rejected
-                bad_hi[r] = hi32(pu) | hi32(pv);
-                none &= bad_lo[r] & bad_hi[r]; // sign bit stays set only if every test of the pair failed
+                pu[r] = ffma2(un[r], fsub2(den[r], un[r]), m);                  // uN (DEN - uN) + m
+                pv[r] = ffma2(vn[r], fsub2(den[r], vn[r]), m);                  // vN (DEN - vN) + m
+                none = or_and(lo32(pu[r]), lo32(pv[r]), none);                  // one LOP3 per test
+                none = or_and(hi32(pu[r]), hi32(pv[r]), none);
             }
             if ((int)none >= 0) { // rare: some (ray, triangle) of this pair passed both product tests
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const unsigned bad = h ? bad_hi[r] : bad_lo[r];
-                        if ((int)bad >= 0) {
+                        // (separate sign tests here keep the fused (a|b)&c LOP3 form in the hot path)
+                        const int su = (int)(h ? hi32(pu[r]) : lo32(pu[r])), sv = (int)(h ? hi32(pv[r]) : lo32(pv[r]));
+                        if (su >= 0 && sv >= 0) {
                             ++n_cand;
                             const long long i = ray0 + (long long)r * THREADS;
                             const int j = 2 * p + h;
