@@ -38,6 +38,11 @@ constexpr int TILE_TRIS = 128;                  // triangles per tile
 constexpr int TILE_F4 = TILE_TRIS * 4;          // float4 per tile
 constexpr int TILE_BYTES = TILE_TRIS * 64;      // 8 KB
 constexpr int STAGES = 4;                       // TMA pipeline depth
+#ifndef LPCL_PAIR_UNROLL
+#define LPCL_PAIR_UNROLL 4                      // unroll factor of the triangle-pair loop (measured: 1 -> 4 = +3%)
+#endif
+#define LPCL_STR_(x) #x
+#define LPCL_UNROLL(n) _Pragma(LPCL_STR_(unroll n))
 
 struct TileInfo {
     int tri0;   // global index of the tile's first triangle
@@ -320,7 +325,7 @@ search_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *
         const ulonglong2 *tb = reinterpret_cast<const ulonglong2 *>(tile_buf + stage * TILE_F4);
         const int npairs = (count + 1) >> 1;
 
-#pragma unroll 1
+        LPCL_UNROLL(LPCL_PAIR_UNROLL)
         for (int p = 0; p < npairs; ++p) {
             // 8 x LDS.128 (warp-uniform address => broadcast): 16 components x 2 triangles
             const ulonglong2 l0 = tb[p * 8 + 0], l1 = tb[p * 8 + 1], l2 = tb[p * 8 + 2], l3 = tb[p * 8 + 3];
