@@ -8,8 +8,8 @@
 //       refracted, parent order kept - exactly the order NumPy pruning produces at
 //       iterative_tracer.py:366-373) and of the measured parents (get_measured_rays order,
 //       it:395-411).  The three exclusive prefixes come from a single-pass chained scan
-//       (decoupled look-back): a block publishes its aggregate, then inspects its predecessors;
-//       block ids are handed out by an atomic ticket so a predecessor is always resident.
+//       (decoupled look-back): a block publishes its aggregate, then inspects its predecessors
+//       (lower blockIdx.x, dispatched earlier, hence always resident or finished).
 //       HBM-bound: ~44 B read + 48 B triangle gather + 16 B result + 32(+8) B per child.
 #pragma once
 
@@ -17,7 +17,10 @@
 
 namespace lpcl {
 
-constexpr int STEP_THREADS = 256;
+#ifndef LPCL_STEP_THREADS
+#define LPCL_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = LPCL_STEP_THREADS;
 
 struct StepCounters { // mirrors lpcl_step_counters
     long long n_reflect, n_refract, n_measured, n_terminated;
@@ -171,15 +174,16 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
             long long meas_cap, StepCounters *ctr,
             unsigned long long *words, unsigned *ticket, float max_ray_len, float ior_env, int iteration)
 {
-    __shared__ unsigned s_bid;
     __shared__ unsigned s_warp[3][STEP_THREADS / 32];
     __shared__ unsigned long long s_excl[2];
     __shared__ double s_pow[2][STEP_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int bid = (int)s_bid;
+    // Block id = blockIdx.x: the look-back only ever waits on LOWER block ids, which a 1-D grid
+    // dispatches first (the assumption CUB's single-pass scan makes too).  An atomic ticket was
+    // measured to cost half of the kernel (3,907 same-address atomics serialise in L2).
+    (void)ticket;
+    const int bid = (int)blockIdx.x;
     const long long n = par.n;
     const long long i = (long long)bid * STEP_THREADS + tid;
     const bool valid = i < n;
@@ -199,13 +203,37 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
         const V3 o = v3(o4.x, o4.y, o4.z), d = v3(d4.x, d4.y, d4.z);
         const int prev = __float_as_int(d4.w);
         const int M = sc.mesh_count;
-        auto fetch = [&](int j, float &t, int &h, int &tri) {
-            unsigned long long k = key[(long long)j * n + i];
-            t = key_t(k);
-            tri = key_tri(k);
-            h = cnt[(long long)j * n + i];
-        };
-        const Resolve r = resolve_media(M, prev, sc.mat_type, max_ray_len, fetch);
+        if (par.lineage) lin = par.lineage[ph];
+        Resolve r;
+        constexpr int MREG = 8;
+        if (M <= MREG) {
+            // few meshes (every BASELINE config): issue all 2M scratch loads at once, resolve from registers
+            unsigned long long kreg[MREG];
+            int creg[MREG];
+#pragma unroll
+            for (int j = 0; j < MREG; ++j) {
+                kreg[j] = 0;
+                creg[j] = 0;
+                if (j < M) {
+                    kreg[j] = key[(long long)j * n + i];
+                    creg[j] = cnt[(long long)j * n + i];
+                }
+            }
+            auto fetch = [&](int j, float &t, int &h, int &tri) {
+                t = key_t(kreg[j]);
+                tri = key_tri(kreg[j]);
+                h = creg[j];
+            };
+            r = resolve_media<MREG>(M, prev, sc.mat_type, max_ray_len, fetch);
+        } else {
+            auto fetch = [&](int j, float &t, int &h, int &tri) {
+                unsigned long long k = key[(long long)j * n + i];
+                t = key_t(k);
+                tri = key_tri(k);
+                h = cnt[(long long)j * n + i];
+            };
+            r = resolve_media<0>(M, prev, sc.mat_type, max_ray_len, fetch);
+        }
         end = ray_end(o, d, r.t);
         auto tri = [&](int t, V3 &a, V3 &b, V3 &c) {
             float4 fa = __ldg(sc.v0 + t), fb = __ldg(sc.v1 + t), fc = __ldg(sc.v2 + t);
@@ -223,7 +251,6 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
         keep_t = s.refr.measured == 0;
         is_meas = s.measured == 1;
         is_term = s.measured == -1;
-        if (par.lineage) lin = par.lineage[ph];
     }
 
     // block-level exclusive ranks of the three flags

@@ -202,7 +202,9 @@ struct Resolve {
 };
 
 // `fetch(j, t_j, hits_j, tri_j)` returns mesh j's nearest distance, crossing count and triangle.
-template <class Fetch>
+// UNROLL > 0: mesh_count <= UNROLL is guaranteed by the caller and both loops are fully unrolled
+// (the per-mesh values then live in registers); UNROLL == 0: plain run-time loops.
+template <int UNROLL = 0, class Fetch>
 LPCL_HD Resolve resolve_media(int mesh_count, int prev_mesh, const int *mat_type, float max_ray_len, Fetch fetch)
 {
     const float eps = eps_len(max_ray_len);
@@ -214,7 +216,10 @@ LPCL_HD Resolve resolve_media(int mesh_count, int prev_mesh, const int *mat_type
     r.n2 = -1;
     r.entering = 0;
     int hits_hit = 0;
-    for (int j = 0; j < mesh_count; ++j) { // cl:127-135, strict '<': lowest mesh id wins ties
+    const int bound = UNROLL > 0 ? UNROLL : mesh_count;
+#pragma unroll
+    for (int j = 0; j < bound; ++j) { // cl:127-135, strict '<': lowest mesh id wins ties
+        if (UNROLL > 0 && j >= mesh_count) break;
         float tj;
         int hj, ij;
         fetch(j, tj, hj, ij);
@@ -240,7 +245,9 @@ LPCL_HD Resolve resolve_media(int mesh_count, int prev_mesh, const int *mat_type
     const float t_edge = LPCL_ADD(t_first, eps);
     float t_a = r.t, t_b = max_ray_len;
     int win_a = -1, win_a_entering = 0, win_b = -1;
-    for (int j = 0; j < mesh_count; ++j) {
+#pragma unroll
+    for (int j = 0; j < bound; ++j) {
+        if (UNROLL > 0 && j >= mesh_count) break;
         int mt = mat_type[j];
         if (mt != 0 && mt != 4) continue; // cl:194
         float tj;
