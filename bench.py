@@ -205,7 +205,7 @@ def main_native(args):
         import torch.distributed as td
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
+        os.environ.pop("NCCL_DEBUG", None)  # no NCCL banner (stdout is diverted to stderr anyway, see __main__)
         torch.cuda.set_device(local_rank)
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
@@ -371,4 +371,20 @@ def main_native(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_native(a))
+    # stdout carries exactly ONE line (the JSON): anything libraries print meanwhile (e.g. NCCL's
+    # version banner when the image exports NCCL_DEBUG) is diverted to stderr at the fd level
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _orig_print = print
+
+    def print(*args, **kw):  # noqa: A001 - the final JSON line goes to the real stdout
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        _orig_print(*args, **kw)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
+    rc = main_reference(a) if a.impl == "reference" else main_native(a)
+    sys.stdout.flush()
+    sys.exit(rc)
