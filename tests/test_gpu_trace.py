@@ -133,3 +133,43 @@ def test_determinism_and_shard_union_at_scale():
     assert np.array_equal(key(fpos, np.asarray(fpwr).reshape(-1)), key(upos, upwr))
     measured = float(np.sum(np.asarray(pa[1], np.float64)))
     assert 0.3 * a.input_power < measured <= a.input_power * (1 + 1e-5)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("c5_lenslet_array", dict(ray_count=60, sources=4, grid=3, ang_pts=9, per_lenslet_mesh=True)),  # 11 meshes > 8
+    ("c5_lenslet_array", dict(ray_count=40, sources=1, grid=4, ang_pts=5, per_lenslet_mesh=True)),  # 18 meshes
+])
+def test_many_meshes_take_the_generic_resolve_path(name, kw):
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.CONFIGS[name](**kw)
+    assert len(meshes) > 8
+    _check(name, ls, meshes, dict(params, trace_iterations=6))
+
+
+def test_edge_cases_single_ray_all_miss_and_tiny_scene():
+    from lightpycl_b200 import geo_optical_elements as goe, light_source as lsm
+
+    oe = goe.optical_elements()
+    plate = oe.cube(center=(0, 0, 10, 0), size=[2, 2, 1, 0])
+    plate.setMaterial(mat_type="measure")
+    params = dict(trace_iterations=5, trace_until_dissipated=0.99, max_ray_len=np.float32(100.0), ior_env=np.float32(1.0))
+    # one ray straight at the plate
+    one = util.ArraySource(np.array([[0.1, 0.2, 0, 0]], np.float32), np.array([[0, 0, 1, 0]], np.float32),
+                           np.array([2.5], np.float32))
+    tr, ref = _check("one ray", [one], [plate], params)
+    assert tr.results.ray_counts == [1] and tr.stats["measured"] == [1]
+    # every ray misses everything: one generation, all terminated, nothing measured
+    np.random.seed(2)
+    away = lsm.light_source(center=np.array([0, 0, 0, 0], np.float32), direction=(0, 0, -1), ray_count=777, power=3.0)
+    tr, ref = _check("all miss", [away], [plate], params)
+    assert tr.results.ray_counts == [777] and tr.stats["terminated"] == [777] and tr.stats["live"] == [0]
+    pos, pwr = tr.get_measured_rays()
+    assert pos.shape == (0, 4) and np.asarray(pwr).size == 0
+    # rays exactly along a face of a cube (parallel, DEN == 0) and through an edge shared by two triangles
+    box = oe.cube(center=(0, 0, 5, 0), size=[2, 2, 2, 0])
+    box.setMaterial(mat_type="refractive", IOR=1.5)
+    o = np.array([[1.0, 0.0, 0, 0], [0.0, 0.0, 0, 0], [0.5, 0.5, 0, 0], [-1.0, -1.0, 0, 0]], np.float32)
+    d = np.tile(np.array([[0, 0, 1, 0]], np.float32), (4, 1))
+    graze = util.ArraySource(o, d, np.ones(4, np.float32))
+    _check("grazing", [graze], [plate, box], params)
