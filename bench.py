@@ -276,7 +276,7 @@ def main_native(args):
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 3))
-        times, h2d, d2h, rays_e2e = [], 0, 0, 0
+        times, h2d, d2h, rays_e2e, breakdown = [], 0, 0, 0, []
         tr2 = it.CL_Tracer(platform_name="NVIDIA", device_name="B200", device=device, keep_results=False,
                            shard_input=False)
         tr2.iterative_tracer(ls, meshes, **params)  # warm-up (allocator, scene)
@@ -286,9 +286,14 @@ def main_native(args):
             torch.cuda.synchronize(device)
             t0 = time.perf_counter()
             tr2.iterative_tracer(ls, meshes, **params)
+            t1 = time.perf_counter()
             pos, pwr = tr2.get_measured_rays(gather=False)
             torch.cuda.synchronize(device)
             times.append(time.perf_counter() - t0)
+            breakdown.append({"host_flatten_ms": round(1e3 * tr2.timings.get("host_flatten_s", 0.0), 2),
+                              "upload_and_scene_ms": round(1e3 * tr2.timings.get("upload_s", 0.0), 2),
+                              "device_loop_ms": round(1e3 * tr2.timings.get("run_s", 0.0), 2),
+                              "measured_download_ms": round(1e3 * (time.perf_counter() - t1), 2)})
             h2d = tr2.h2d_bytes
             d2h = int(pos.shape[0] * 16 + 64 * len(tr2.stats["rays"]))
             rays_e2e = sum(tr2.stats["rays"])
@@ -297,7 +302,7 @@ def main_native(args):
         e2e_tests = sum_over_ranks(float(rays_e2e * e2e_steps)) * tri
         e2e = {"value": e2e_tests / t_e2e, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
-               "traced_rays_per_s": e2e_tests / tri / t_e2e}
+               "traced_rays_per_s": e2e_tests / tri / t_e2e, "breakdown_per_step": breakdown}
 
     if rank != 0:
         if world > 1:

@@ -68,6 +68,14 @@ int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const float *d_v1, co
                       const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
                       const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
                       void *stream);
+/* Same, but the device memory of the handle (filter tiles, tile table, materials) is a caller-owned
+ * buffer of at least lpcl_scene_bytes(tri_count, mesh_count) bytes, 256-byte aligned, that must
+ * outlive the handle: nothing is cudaMalloc'ed or cudaFree'd (the allocator stays the caller's). */
+int64_t lpcl_scene_bytes(int32_t tri_count, int32_t mesh_count);
+int lpcl_scene_create_in(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
+                         const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
+                         const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
+                         void *d_scene_mem, int64_t scene_mem_bytes, void *stream);
 void lpcl_scene_destroy(lpcl_scene *scene);
 int32_t lpcl_scene_tri_count(const lpcl_scene *scene);
 int32_t lpcl_scene_mesh_count(const lpcl_scene *scene);

@@ -53,6 +53,8 @@ SYMBOLS = {
     "lpcl_abi_version": (C.c_int, []),
     "lpcl_last_error": (C.c_char_p, []),
     "lpcl_scene_create": (C.c_int, [C.POINTER(_p), _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
+    "lpcl_scene_bytes": (_i64, [_i32, _i32]),
+    "lpcl_scene_create_in": (C.c_int, [C.POINTER(_p), _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     "lpcl_scene_destroy": (None, [_p]),
     "lpcl_scene_tri_count": (_i32, [_p]),
     "lpcl_scene_mesh_count": (_i32, [_p]),

@@ -62,10 +62,25 @@ extern "C" const char *lpcl_last_error(void) { return g_err; }
 
 static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
-                                 const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
-                                 const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
-                                 void *stream_)
+// upper bound of the device bytes a scene needs: tiles never straddle meshes, so at most
+// ceil(T / TILE_TRIS) + mesh_count tiles
+static int64_t scene_bytes_bound(int64_t tri_count, int64_t mesh_count)
+{
+    const int64_t max_tiles = (tri_count + TILE_TRIS - 1) / TILE_TRIS + mesh_count;
+    return align_up(max_tiles * TILE_BYTES, 256) + align_up(max_tiles * (int64_t)sizeof(TileInfo), 256) +
+           4 * align_up(mesh_count * 4, 256) + 256;
+}
+
+extern "C" int64_t lpcl_scene_bytes(int32_t tri_count, int32_t mesh_count)
+{
+    if (tri_count <= 0 || mesh_count <= 0) return 0;
+    return scene_bytes_bound(tri_count, mesh_count);
+}
+
+static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
+                             const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
+                             const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
+                             void *d_mem, int64_t mem_bytes, bool borrow, void *stream_)
 {
     if (!out || !d_v0 || !d_v1 || !d_v2 || !h_tri_mesh || !h_mat_type || !h_ior || !h_refl || !h_diss)
         return fail(LPCL_E_NULL, "lpcl_scene_create: NULL argument");
@@ -112,13 +127,24 @@ extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const floa
     const int64_t off_diss = off_refl + align_up((int64_t)mesh_count * 4, 256);
     const int64_t off_vmax = off_diss + align_up((int64_t)mesh_count * 4, 256);
     const int64_t total = off_vmax + 256;
-    cudaError_t e = cudaMalloc(&sc->owned, (size_t)total);
-    if (e != cudaSuccess) {
-        delete sc;
-        return fail((int)e, "cudaMalloc(%lld): %s", (long long)total, cudaGetErrorString(e));
+    char *base = nullptr;
+    if (borrow) { // caller-owned memory (e.g. a torch tensor): no cudaMalloc / cudaFree on this path
+        if (!d_mem || mem_bytes < total || (reinterpret_cast<uintptr_t>(d_mem) & 255u)) {
+            delete sc;
+            return fail(d_mem ? LPCL_E_RANGE : LPCL_E_NULL, "lpcl_scene_create_in: need %lld bytes of 256-byte aligned device memory",
+                        (long long)total);
+        }
+        base = (char *)d_mem;
+        sc->owned = nullptr;
+    } else {
+        cudaError_t e = cudaMalloc(&sc->owned, (size_t)total);
+        if (e != cudaSuccess) {
+            delete sc;
+            return fail((int)e, "cudaMalloc(%lld): %s", (long long)total, cudaGetErrorString(e));
+        }
+        base = (char *)sc->owned;
     }
     sc->owned_bytes = total;
-    char *base = (char *)sc->owned;
     SceneDev &d = sc->dev;
     d.v0 = (const float4 *)d_v0;
     d.v1 = (const float4 *)d_v1;
@@ -138,7 +164,7 @@ extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const floa
     do {                                                                                 \
         cudaError_t e__ = (expr);                                                        \
         if (e__ != cudaSuccess) {                                                        \
-            cudaFree(sc->owned);                                                         \
+            if (sc->owned) cudaFree(sc->owned);                                          \
             delete sc;                                                                   \
             return fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__));             \
         }                                                                                \
@@ -166,6 +192,24 @@ extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const floa
 #undef SCENE_TRY
     *out = sc;
     return 0;
+}
+
+extern "C" int lpcl_scene_create(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
+                                 const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
+                                 const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
+                                 void *stream_)
+{
+    return scene_create_impl(out, d_v0, d_v1, d_v2, h_tri_mesh, tri_count, h_mat_type, h_ior, h_refl, h_diss, mesh_count,
+                             nullptr, 0, false, stream_);
+}
+
+extern "C" int lpcl_scene_create_in(lpcl_scene **out, const float *d_v0, const float *d_v1, const float *d_v2,
+                                    const int32_t *h_tri_mesh, int32_t tri_count, const int32_t *h_mat_type,
+                                    const float *h_ior, const float *h_refl, const float *h_diss, int32_t mesh_count,
+                                    void *d_scene_mem, int64_t scene_mem_bytes, void *stream_)
+{
+    return scene_create_impl(out, d_v0, d_v1, d_v2, h_tri_mesh, tri_count, h_mat_type, h_ior, h_refl, h_diss, mesh_count,
+                             d_scene_mem, scene_mem_bytes, true, stream_);
 }
 
 extern "C" void lpcl_scene_destroy(lpcl_scene *scene)

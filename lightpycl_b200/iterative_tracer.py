@@ -50,6 +50,8 @@ def flatten_light_sources(light_source):
     shapes = {p.ndim for p in powers}
     if len(shapes) != 1:  # np.append(..., axis=0) of (N,1) and (N,) raises in the reference too (it:111)
         raise ValueError("all light sources must give rays_power with the same number of dimensions")
+    if len(origins) == 1:  # one source: no copy (the arrays are only read)
+        return np.ascontiguousarray(origins[0]), np.ascontiguousarray(dirs[0]), np.ascontiguousarray(powers[0])
     origin = np.ascontiguousarray(np.concatenate(origins, axis=0))
     direc = np.ascontiguousarray(np.concatenate(dirs, axis=0))
     power = np.ascontiguousarray(np.concatenate(powers, axis=0))
@@ -59,7 +61,9 @@ def flatten_light_sources(light_source):
 def sorted_sequential_sum_f32(p):
     """``sum(np.sort(p))`` as the reference evaluates it (it:115): sort along the last axis, then
     a left-to-right float32 accumulation (np.cumsum accumulates sequentially)."""
-    flat = np.sort(np.asarray(p, dtype=np.float32)).reshape(-1)
+    p = np.asarray(p, dtype=np.float32)
+    # np.sort works along the LAST axis: a no-op for the (N,1) power of random_rays
+    flat = (p if (p.ndim > 1 and p.shape[-1] == 1) else np.sort(p)).reshape(-1)
     if flat.size == 0:
         return np.float32(0.0)
     return np.float32(np.cumsum(flat, dtype=np.float32)[-1])
@@ -249,14 +253,19 @@ class CL_Tracer:
         torch = self._torch
         self._release_scene()
         dev = {k: torch.from_numpy(flat[k]).to(self.device, non_blocking=False) for k in ("v0", "v1", "v2")}
+        # the handle's device memory comes from torch's caching allocator (no cudaMalloc/cudaFree per trace)
+        n_tri, n_mesh = len(flat["tri_mesh"]), len(flat["mat_type"])
+        need = int(self._lib.lpcl_scene_bytes(n_tri, n_mesh))
+        dev["scene_mem"] = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        base = (dev["scene_mem"].data_ptr() + 255) // 256 * 256
         handle = C.c_void_p()
-        rc = self._lib.lpcl_scene_create(
+        rc = self._lib.lpcl_scene_create_in(
             C.byref(handle), dev["v0"].data_ptr(), dev["v1"].data_ptr(), dev["v2"].data_ptr(),
-            flat["tri_mesh"].ctypes.data, len(flat["tri_mesh"]), flat["mat_type"].ctypes.data, flat["ior"].ctypes.data,
-            flat["refl"].ctypes.data, flat["diss"].ctypes.data, len(flat["mat_type"]), self._stream())
-        _cabi.check(rc, "lpcl_scene_create")
+            flat["tri_mesh"].ctypes.data, n_tri, flat["mat_type"].ctypes.data, flat["ior"].ctypes.data,
+            flat["refl"].ctypes.data, flat["diss"].ctypes.data, n_mesh, base, need, self._stream())
+        _cabi.check(rc, "lpcl_scene_create_in")
         self._scene = handle
-        self._scene_tensors = dev  # the handle borrows the vertex buffers: keep them alive
+        self._scene_tensors = dev  # the handle borrows the vertex buffers and its own memory: keep them alive
 
     def _get_workspace(self, n):
         torch = self._torch
@@ -359,7 +368,9 @@ class CL_Tracer:
             self.kernel_launches = 0
             self.stats = dict(rays=[], live=[], power_left=[], candidates=[], measured=[], terminated=[])
             counters_dev = torch.zeros(8, dtype=torch.int64, device=self.device)
-            counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+            if getattr(self, "_counters_host", None) is None:  # pinned once per tracer (cudaHostAlloc is slow)
+                self._counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+            counters_host = self._counters_host
 
             gen = None
             if n > 0:
