@@ -1,0 +1,75 @@
+"""The rest of the CL_Tracer surface a LightPyCL script touches after the trace (reference
+it:395-779): lazy `results`, pickling, DXF export, beam metrics - exercised on a small scene."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def traced():
+    from lightpycl_b200 import iterative_tracer as it, scenes
+
+    ls, meshes, params = scenes.parabolic_mirror(ray_count=4000, profile_pts=60, ang_pts=37)
+    tr = it.CL_Tracer(platform_name="NVIDIA", device_name="460")  # reference-style arguments are accepted
+    res = tr.iterative_tracer(light_source=ls, meshes=meshes, **params)
+    assert res is tr.results
+    return tr, ls, meshes, params
+
+
+def test_results_behave_like_the_reference_list(traced):
+    tr, ls, meshes, params = traced
+    res = tr.results
+    assert len(res) == len(res.ray_counts) >= 2
+    proc = sum(len(r[3]) for r in res)  # the loop every reference example runs (ex_lens:86-90)
+    assert proc == sum(res.ray_counts)
+    o, d, p, m = res[0]
+    assert o.shape == (4000, 4) and d.shape == (4000, 4) and p.shape == (4000, 1) and m.dtype == np.int32
+    assert set(np.unique(m)) <= {-1, 0, 1}
+    assert res[-1][0].shape[0] == res.ray_counts[-1] and res[0:1][0][2].shape == (4000, 1)
+    assert int(tr.tri_count) == sum(len(x.triangles) for x in meshes) and len(tr.geometry) == 3
+
+
+def test_pickle_roundtrip_and_dxf(traced, tmp_path, monkeypatch):
+    from lightpycl_b200 import iterative_tracer as it
+
+    tr, ls, meshes, params = traced
+    monkeypatch.chdir(tmp_path)
+    fname = tr.pickle_results()
+    assert fname and os.path.exists(fname)
+    other = it.CL_Tracer()
+    other.load_pickle_results(fname)
+    assert len(other.results) == len(tr.results)
+    for a, b in zip(other.results, tr.results):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    tr.save_traced_scene(str(tmp_path / "scene.dxf"))
+    txt = open(tmp_path / "scene.dxf").read()
+    assert txt.count("3DFACE") == sum(tr.results.ray_counts) + int(tr.tri_count) and txt.rstrip().endswith("EOF")
+    meshes[2].write_dxf(str(tmp_path / "plate.dxf"))
+    assert open(tmp_path / "plate.dxf").read().count("3DFACE") == 12
+    ls[0].save_dxf(str(tmp_path / "rays.dxf"))
+
+
+def test_beam_metrics(traced, capsys):
+    tr, ls, meshes, params = traced
+    total, angle, frac = tr.get_beam_width_half_power(points=100, pole=[0, 0, 1, 0])
+    pos, pwr = tr.get_measured_rays()
+    assert abs(total - float(np.sum(np.asarray(pwr, np.float64)))) <= 1e-9 * total
+    assert 0.0 <= float(angle[0]) <= np.pi / 2 and 0.4 < float(frac[0]) < 0.6
+    total2, hwhm, frac2 = tr.get_beam_HWHM(points=100, pole=[0, 0, 1, 0])
+    assert abs(total2 - total) <= 1e-9 * total and 0.0 <= float(hwhm[0]) <= np.pi / 2
+    x, inten = tr.get_elevation_histogram(points=90, pole=[0, 0, 1, 0])
+    assert x.shape == (90,) and np.all(np.isfinite(inten))
+    out = capsys.readouterr().out
+    assert "Beam halfpower angle" in out and "Beam HWHM angle" in out
+    # a collimated beam from a parabola: almost all measured power within a few degrees of the pole
+    elev = np.arccos(pos[:, 2] / np.linalg.norm(pos[:, :3], axis=1))
+    w = np.asarray(pwr, np.float64).reshape(-1)
+    assert w[elev < np.deg2rad(5)].sum() > 0.9 * w.sum()
