@@ -82,8 +82,29 @@ def report(path, out_dir, tag, note):
             for h in hdr:
                 if h in KEYS or any(h.startswith(p) for p in PREFIXES):
                     f.write("%-92s %-16s %s\n" % (h, u[h], rec[h]))
-    with open(os.path.join(out_dir, "%s_ncu_traffic.json" % tag), "w") as f:
-        json.dump({"note": note, "kernels": traffic}, f, indent=1)
+    return traffic
+
+
+def metrics_csv(path, traffic):
+    """A `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` log:
+    fills in kernels whose dram counters came back NaN in the --set full capture (seen for the 65 us
+    step kernel)."""
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    idx = {h: i for i, h in enumerate(rows[0])}
+    per = {}
+    for r in rows[1:]:
+        short = re.sub(r"[^a-z_]", "", re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("lpcl::", "").split("<")[0])
+        rec = per.setdefault((short, r[idx["ID"]]), {})
+        val = float(r[idx["Metric Value"]].replace(",", "")) * UNIT.get(r[idx["Metric Unit"]], 1)
+        rec[r[idx["Metric Name"]]] = (val, r[idx["Metric Unit"]])
+    for (short, _id), rec in sorted(per.items(), key=lambda kv: int(kv[0][1])):
+        entry = {"dram_read_bytes": rec["dram__bytes_read.sum"][0], "dram_write_bytes": rec["dram__bytes_write.sum"][0],
+                 "duration": rec["gpu__time_duration.sum"][0], "duration_unit": rec["gpu__time_duration.sum"][1],
+                 "source": "metrics-only capture"}
+        cur = traffic.get(short, [])
+        if not cur or cur[0]["dram_read_bytes"] != cur[0]["dram_read_bytes"]:  # absent or NaN
+            traffic[short] = [entry]
+    return traffic
 
 
 if __name__ == "__main__":
@@ -91,6 +112,7 @@ if __name__ == "__main__":
     ap.add_argument("--tag", required=True)
     ap.add_argument("--launches")
     ap.add_argument("--report")
+    ap.add_argument("--metrics-csv", help="metrics-only ncu csv used where the full capture returned NaN dram counters")
     ap.add_argument("--note", default="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e (C3: 1M rays x 100,552 triangles)")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles"))
     a = ap.parse_args()
@@ -98,4 +120,8 @@ if __name__ == "__main__":
     if a.launches:
         launches(a.launches, a.out, a.tag, "ncu --metrics gpu__time_duration.sum --clock-control none; " + a.note)
     if a.report:
-        report(a.report, a.out, a.tag, "ncu --set full --clock-control none; " + a.note)
+        traffic = report(a.report, a.out, a.tag, "ncu --set full --clock-control none; " + a.note)
+        if a.metrics_csv:
+            traffic = metrics_csv(a.metrics_csv, traffic)
+        with open(os.path.join(a.out, "%s_ncu_traffic.json" % a.tag), "w") as f:
+            json.dump({"note": "ncu --set full --clock-control none; " + a.note, "kernels": traffic}, f, indent=1)
