@@ -233,7 +233,7 @@ extern "C" int64_t lpcl_scratch_bytes(const lpcl_scene *s, int64_t n)
     return scratch_key_bytes(s, n) + scratch_cnt_bytes(s, n) + 256;
 }
 
-static int64_t step_blocks(int64_t n) { return (n + STEP_THREADS - 1) / STEP_THREADS; }
+static int64_t step_blocks(int64_t n) { return (n + STEP_RAYS - 1) / STEP_RAYS; }
 
 extern "C" int64_t lpcl_step_workspace_bytes(const lpcl_scene *s, int64_t n)
 {

@@ -21,6 +21,11 @@ namespace lpcl {
 #define LPCL_STEP_THREADS 256
 #endif
 constexpr int STEP_THREADS = LPCL_STEP_THREADS;
+#ifndef LPCL_STEP_ITEMS
+#define LPCL_STEP_ITEMS 2                        // measured on B200 (C3, 1M rays): 1 -> 80 us, 2 -> 70 us, 4 -> 74 us
+#endif
+constexpr int STEP_ITEMS = LPCL_STEP_ITEMS;      // rays per thread of the step kernel
+constexpr int STEP_RAYS = STEP_THREADS * STEP_ITEMS;
 
 struct StepCounters { // mirrors lpcl_step_counters
     long long n_reflect, n_refract, n_measured, n_terminated;
@@ -167,6 +172,17 @@ __device__ __forceinline__ void chained_scan(unsigned long long *words, int bid,
 }
 
 // ------------------------------------------------------------------------------------------ production step
+// One thread handles STEP_ITEMS rays: item k of thread tid is ray  block0 + k*STEP_THREADS + tid
+// (coalesced per item).  One block-wide scan and ONE look-back serve STEP_THREADS*STEP_ITEMS rays,
+// and the independent items give the memory system several loads in flight per thread.
+struct StepItem {
+    V3 end, rdir, tdir;        // end point, reflected / refracted direction
+    float rpow, tpow, ppow;    // child powers, parent power after dissipation
+    int hit_mesh;
+    unsigned long long lin;
+    unsigned bits;             // [0] keep_r [1] keep_t [2] measured [3] terminated | rank_r<<8 | rank_t<<16 | rank_m<<24
+};
+
 __global__ void __launch_bounds__(STEP_THREADS)
 step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__restrict__ key,
             const int *__restrict__ cnt, float4 *__restrict__ dest_meas, int4 *__restrict__ hit_out,
@@ -174,132 +190,159 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
             long long meas_cap, StepCounters *ctr,
             unsigned long long *words, unsigned *ticket, float max_ray_len, float ior_env, int iteration)
 {
-    __shared__ unsigned s_warp[3][STEP_THREADS / 32];
-    __shared__ unsigned long long s_excl[2];
-    __shared__ double s_pow[2][STEP_THREADS / 32];
+    constexpr int NW = STEP_THREADS / 32;          // warps per block
+    constexpr int SLOTS = NW * STEP_ITEMS;         // (item, warp) pairs in ray order, item-major
+    static_assert(SLOTS <= 32, "the (item, warp) totals are scanned by one warp");
+    __shared__ unsigned s_cnt[3][SLOTS];           // per (item, warp): survivors / measured
+    __shared__ unsigned s_off[3][SLOTS];           // their exclusive prefix inside the block
+    __shared__ unsigned long long s_excl[2];       // block-exclusive prefixes from the look-back
+    __shared__ double s_pow[2][NW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Block id = blockIdx.x: the look-back only ever waits on LOWER block ids, which a 1-D grid
-    // dispatches first (the assumption CUB's single-pass scan makes too).  An atomic ticket was
-    // measured to cost half of the kernel (3,907 same-address atomics serialise in L2).
+    // dispatches first (the assumption CUB's single-pass scan makes too).
     (void)ticket;
     const int bid = (int)blockIdx.x;
     const long long n = par.n;
-    const long long i = (long long)bid * STEP_THREADS + tid;
-    const bool valid = i < n;
+    const long long block0 = (long long)bid * (STEP_THREADS * STEP_ITEMS);
+    const int M = sc.mesh_count;
+    const unsigned below = (1u << lane) - 1u;
 
-    bool keep_r = false, keep_t = false, is_meas = false, is_term = false;
-    V3 end = v3(0.f, 0.f, 0.f);
-    Scatter s;
-    s.power = 0.f;
-    s.refl.power = s.refr.power = 0.f;
-    s.refl.dir = s.refr.dir = v3(0.f, 0.f, 0.f);
-    int hit_mesh = -1;
-    unsigned long long lin = 0;
+    StepItem it[STEP_ITEMS];
+    double lp = 0.0, mp = 0.0;
+    unsigned n_term = 0;
 
-    if (valid) {
-        const long long ph = par.phys(i);
-        const float4 o4 = par.org_pow[ph], d4 = par.dir_prev[ph];
-        const V3 o = v3(o4.x, o4.y, o4.z), d = v3(d4.x, d4.y, d4.z);
-        const int prev = __float_as_int(d4.w);
-        const int M = sc.mesh_count;
-        if (par.lineage) lin = par.lineage[ph];
-        Resolve r;
-        constexpr int MREG = 8;
-        if (M <= MREG) {
-            // few meshes (every BASELINE config): issue all 2M scratch loads at once, resolve from registers
-            unsigned long long kreg[MREG];
-            int creg[MREG];
+    // ray state of every item first: STEP_ITEMS independent 2 x 16-byte loads in flight
+    float4 o4[STEP_ITEMS], d4[STEP_ITEMS];
+    long long ph[STEP_ITEMS];
 #pragma unroll
-            for (int j = 0; j < MREG; ++j) {
-                kreg[j] = 0;
-                creg[j] = 0;
-                if (j < M) {
-                    kreg[j] = key[(long long)j * n + i];
-                    creg[j] = cnt[(long long)j * n + i];
-                }
-            }
-            auto fetch = [&](int j, float &t, int &h, int &tri) {
-                t = key_t(kreg[j]);
-                tri = key_tri(kreg[j]);
-                h = creg[j];
-            };
-            r = resolve_media<MREG>(M, prev, sc.mat_type, max_ray_len, fetch);
-        } else {
-            auto fetch = [&](int j, float &t, int &h, int &tri) {
-                unsigned long long k = key[(long long)j * n + i];
-                t = key_t(k);
-                tri = key_tri(k);
-                h = cnt[(long long)j * n + i];
-            };
-            r = resolve_media<0>(M, prev, sc.mat_type, max_ray_len, fetch);
-        }
-        end = ray_end(o, d, r.t);
-        auto tri = [&](int t, V3 &a, V3 &b, V3 &c) {
-            float4 fa = __ldg(sc.v0 + t), fb = __ldg(sc.v1 + t), fc = __ldg(sc.v2 + t);
-            a = v3(fa.x, fa.y, fa.z);
-            b = v3(fb.x, fb.y, fb.z);
-            c = v3(fc.x, fc.y, fc.z);
-        };
-        s = scatter(o, end, d, o4.w, 0, r.n1, r.n2, r.hit_mesh, r.hit_tri, sc.mat_type, sc.ior, sc.refl, sc.diss,
-                    ior_env, tri);
-        hit_mesh = r.hit_mesh;
-        dest_meas[i] = make_float4(end.x, end.y, end.z, __int_as_float(s.measured));
-        if (hit_out) hit_out[i] = make_int4(r.hit_mesh, r.hit_tri, r.n1, r.n2);
-        if (s.power_changed) par.org_pow[ph].w = s.power; // cl:392
-        keep_r = s.refl.measured == 0;
-        keep_t = s.refr.measured == 0;
-        is_meas = s.measured == 1;
-        is_term = s.measured == -1;
+    for (int k = 0; k < STEP_ITEMS; ++k) {
+        const long long i = block0 + (long long)k * STEP_THREADS + tid;
+        ph[k] = par.phys(i < n ? i : n - 1);
+        o4[k] = par.org_pow[ph[k]];
+        d4[k] = par.dir_prev[ph[k]];
+        it[k].lin = par.lineage ? par.lineage[ph[k]] : 0ull;
     }
 
-    // block-level exclusive ranks of the three flags
-    const unsigned br = __ballot_sync(0xffffffffu, keep_r), bt = __ballot_sync(0xffffffffu, keep_t),
-                   bm = __ballot_sync(0xffffffffu, is_meas), bx = __ballot_sync(0xffffffffu, is_term);
-    const unsigned below = (1u << lane) - 1u;
-    unsigned rank_r = __popc(br & below), rank_t = __popc(bt & below), rank_m = __popc(bm & below);
-    double lp = (keep_r ? (double)s.refl.power : 0.0) + (keep_t ? (double)s.refr.power : 0.0);
-    double mp = is_meas ? (double)s.power : 0.0;
+#pragma unroll
+    for (int k = 0; k < STEP_ITEMS; ++k) {
+        const long long i = block0 + (long long)k * STEP_THREADS + tid;
+        const bool valid = i < n;
+        bool keep_r = false, keep_t = false, is_meas = false, is_term = false;
+        it[k].end = it[k].rdir = it[k].tdir = v3(0.f, 0.f, 0.f);
+        it[k].rpow = it[k].tpow = it[k].ppow = 0.f;
+        it[k].hit_mesh = -1;
+        if (valid) {
+            const V3 o = v3(o4[k].x, o4[k].y, o4[k].z), d = v3(d4[k].x, d4[k].y, d4[k].z);
+            const int prev = __float_as_int(d4[k].w);
+            Resolve r;
+            constexpr int MREG = 8;
+            if (M <= MREG) {
+                // few meshes (every BASELINE config): issue all 2M scratch loads at once, resolve from registers
+                unsigned long long kreg[MREG];
+                int creg[MREG];
+#pragma unroll
+                for (int j = 0; j < MREG; ++j) {
+                    kreg[j] = 0;
+                    creg[j] = 0;
+                    if (j < M) {
+                        kreg[j] = key[(long long)j * n + i];
+                        creg[j] = cnt[(long long)j * n + i];
+                    }
+                }
+                auto fetch = [&](int j, float &t, int &h, int &tri) {
+                    t = key_t(kreg[j]);
+                    tri = key_tri(kreg[j]);
+                    h = creg[j];
+                };
+                r = resolve_media<MREG>(M, prev, sc.mat_type, max_ray_len, fetch);
+            } else {
+                auto fetch = [&](int j, float &t, int &h, int &tri) {
+                    unsigned long long kk = key[(long long)j * n + i];
+                    t = key_t(kk);
+                    tri = key_tri(kk);
+                    h = cnt[(long long)j * n + i];
+                };
+                r = resolve_media<0>(M, prev, sc.mat_type, max_ray_len, fetch);
+            }
+            const V3 end = ray_end(o, d, r.t);
+            auto tri = [&](int t, V3 &a, V3 &b, V3 &c) {
+                float4 fa = __ldg(sc.v0 + t), fb = __ldg(sc.v1 + t), fc = __ldg(sc.v2 + t);
+                a = v3(fa.x, fa.y, fa.z);
+                b = v3(fb.x, fb.y, fb.z);
+                c = v3(fc.x, fc.y, fc.z);
+            };
+            const Scatter s = scatter(o, end, d, o4[k].w, 0, r.n1, r.n2, r.hit_mesh, r.hit_tri, sc.mat_type, sc.ior,
+                                      sc.refl, sc.diss, ior_env, tri);
+            dest_meas[i] = make_float4(end.x, end.y, end.z, __int_as_float(s.measured));
+            if (hit_out) hit_out[i] = make_int4(r.hit_mesh, r.hit_tri, r.n1, r.n2);
+            if (s.power_changed) par.org_pow[ph[k]].w = s.power; // cl:392
+            keep_r = s.refl.measured == 0;
+            keep_t = s.refr.measured == 0;
+            is_meas = s.measured == 1;
+            is_term = s.measured == -1;
+            it[k].end = end;
+            it[k].rdir = s.refl.dir;
+            it[k].tdir = s.refr.dir;
+            it[k].rpow = s.refl.power;
+            it[k].tpow = s.refr.power;
+            it[k].ppow = s.power;
+            it[k].hit_mesh = r.hit_mesh;
+            lp += (keep_r ? (double)s.refl.power : 0.0) + (keep_t ? (double)s.refr.power : 0.0);
+            mp += is_meas ? (double)s.power : 0.0;
+        }
+        // ranks inside this (item, warp) slot
+        const unsigned br = __ballot_sync(0xffffffffu, keep_r), bt = __ballot_sync(0xffffffffu, keep_t),
+                       bm = __ballot_sync(0xffffffffu, is_meas), bx = __ballot_sync(0xffffffffu, is_term);
+        it[k].bits = (keep_r ? 1u : 0u) | (keep_t ? 2u : 0u) | (is_meas ? 4u : 0u) | (__popc(br & below) << 8) |
+                     (__popc(bt & below) << 16) | (__popc(bm & below) << 24);
+        if (lane == 0) {
+            s_cnt[0][k * NW + warp] = __popc(br);
+            s_cnt[1][k * NW + warp] = __popc(bt);
+            s_cnt[2][k * NW + warp] = __popc(bm);
+            n_term += __popc(bx);
+        }
+    }
     for (int o = 16; o; o >>= 1) {
         lp += __shfl_xor_sync(0xffffffffu, lp, o);
         mp += __shfl_xor_sync(0xffffffffu, mp, o);
     }
     if (lane == 0) {
-        s_warp[0][warp] = __popc(br);
-        s_warp[1][warp] = __popc(bt);
-        s_warp[2][warp] = __popc(bm);
         s_pow[0][warp] = lp;
         s_pow[1][warp] = mp;
-        if (bx) atomicAdd((unsigned long long *)&ctr->n_terminated, (unsigned long long)__popc(bx));
+        if (n_term) atomicAdd((unsigned long long *)&ctr->n_terminated, (unsigned long long)n_term);
     }
     __syncthreads();
-    unsigned tot_r = 0, tot_t = 0, tot_m = 0;
-#pragma unroll
-    for (int w = 0; w < STEP_THREADS / 32; ++w) {
-        const unsigned a = s_warp[0][w], b = s_warp[1][w], c = s_warp[2][w];
-        if (w < warp) {
-            rank_r += a;
-            rank_t += b;
-            rank_m += c;
-        }
-        tot_r += a;
-        tot_t += b;
-        tot_m += c;
-    }
+
     if (warp == 0) {
+        // exclusive scan of the SLOTS (item, warp) totals, then one look-back for the whole block
+        unsigned v[3], inc[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            v[f] = lane < SLOTS ? s_cnt[f][lane] : 0u;
+            inc[f] = v[f];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc[f], o);
+                if (lane >= o) inc[f] += t;
+            }
+            if (lane < SLOTS) s_off[f][lane] = inc[f] - v[f];
+        }
+        const unsigned tot_r = __shfl_sync(0xffffffffu, inc[0], 31), tot_t = __shfl_sync(0xffffffffu, inc[1], 31),
+                       tot_m = __shfl_sync(0xffffffffu, inc[2], 31);
         unsigned long long ea, eb;
         chained_scan(words, bid, lane, ((unsigned long long)tot_r << 31) | tot_t, tot_m, ea, eb);
         if (lane == 0) {
             s_excl[0] = ea;
             s_excl[1] = eb;
             double blp = 0.0, bmp = 0.0;
-            for (int w = 0; w < STEP_THREADS / 32; ++w) {
+            for (int w = 0; w < NW; ++w) {
                 blp += s_pow[0][w];
                 bmp += s_pow[1][w];
             }
             if (blp != 0.0) atomicAdd(&ctr->live_power, blp);
             if (bmp != 0.0) atomicAdd(&ctr->measured_power, bmp);
-            if ((long long)(bid + 1) * STEP_THREADS >= n) { // last block: inclusive prefixes are the totals
+            if (block0 + (long long)STEP_THREADS * STEP_ITEMS >= n) { // last block: inclusive prefixes are the totals
                 ctr->n_reflect = (long long)(ea >> 31) + tot_r;
                 ctr->n_refract = (long long)(ea & 0x7fffffffull) + tot_t;
                 ctr->n_measured = (long long)eb + tot_m;
@@ -310,23 +353,28 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
     const long long base_r = (long long)(s_excl[0] >> 31), base_t = (long long)(s_excl[0] & 0x7fffffffull);
     const long long base_m = (long long)s_excl[1];
 
-    if (keep_r) { // reflected survivors: first segment of the next generation
-        const long long c = base_r + rank_r;
-        chi.org_pow[c] = make_float4(end.x, end.y, end.z, s.refl.power);
-        chi.dir_prev[c] = make_float4(s.refl.dir.x, s.refl.dir.y, s.refl.dir.z, __int_as_float(hit_mesh));
-        if (chi.lineage) chi.lineage[c] = lin;
-    }
-    if (keep_t) { // refracted survivors: second segment, starting at physical index n
-        const long long c = n + base_t + rank_t;
-        chi.org_pow[c] = make_float4(end.x, end.y, end.z, s.refr.power);
-        chi.dir_prev[c] = make_float4(s.refr.dir.x, s.refr.dir.y, s.refr.dir.z, __int_as_float(hit_mesh));
-        if (chi.lineage) chi.lineage[c] = (iteration < 31) ? (lin | (1ull << (32 + iteration))) : lin;
-    }
-    if (is_meas && meas_out) {
-        const long long c = meas_base + base_m + rank_m;
-        if (c < meas_cap) {
-            meas_out[c] = make_float4(end.x, end.y, end.z, s.power);
-            if (meas_lineage) meas_lineage[c] = lin;
+#pragma unroll
+    for (int k = 0; k < STEP_ITEMS; ++k) {
+        const unsigned bits = it[k].bits;
+        const int slot = k * NW + warp;
+        if (bits & 1u) { // reflected survivors: first segment of the next generation
+            const long long c = base_r + s_off[0][slot] + ((bits >> 8) & 0xffu);
+            chi.org_pow[c] = make_float4(it[k].end.x, it[k].end.y, it[k].end.z, it[k].rpow);
+            chi.dir_prev[c] = make_float4(it[k].rdir.x, it[k].rdir.y, it[k].rdir.z, __int_as_float(it[k].hit_mesh));
+            if (chi.lineage) chi.lineage[c] = it[k].lin;
+        }
+        if (bits & 2u) { // refracted survivors: second segment, starting at physical index n
+            const long long c = n + base_t + s_off[1][slot] + ((bits >> 16) & 0xffu);
+            chi.org_pow[c] = make_float4(it[k].end.x, it[k].end.y, it[k].end.z, it[k].tpow);
+            chi.dir_prev[c] = make_float4(it[k].tdir.x, it[k].tdir.y, it[k].tdir.z, __int_as_float(it[k].hit_mesh));
+            if (chi.lineage) chi.lineage[c] = (iteration < 31) ? (it[k].lin | (1ull << (32 + iteration))) : it[k].lin;
+        }
+        if ((bits & 4u) && meas_out) {
+            const long long c = meas_base + base_m + s_off[2][slot] + ((bits >> 24) & 0xffu);
+            if (c < meas_cap) {
+                meas_out[c] = make_float4(it[k].end.x, it[k].end.y, it[k].end.z, it[k].ppow);
+                if (meas_lineage) meas_lineage[c] = it[k].lin;
+            }
         }
     }
 }
