@@ -334,8 +334,9 @@ struct Scatter {
 
 LPCL_HD float exp_neg(float x)
 {
-    // cl:391 exp() in float.  Evaluated as a correctly rounded double exp rounded to float, which
-    // agrees with glibc's expf (itself a double-precision kernel) outside ~2^-29 of the inputs.
+    // cl:391 exp() of a float.  OpenCL bounds it to 3 ulp only; the oracle pins it as the CORRECTLY
+    // ROUNDED float exponential = double exp rounded to float (oracle/cl_shim.h).  CUDA's double
+    // exp (<= 1 ulp in double) gives the same float outside ~2^-28 of the inputs.
     return (float)exp((double)x);
 }
 

@@ -11,6 +11,9 @@
  *   - cross(a,b) = (a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x)
  *   - length(a)  = sqrtf(dot(a,a));  normalize(a) = a / length(a)
  *   - pown(x,2)  = x*x (float)
+ *   - exp(float) = correctly rounded: (float)exp((double)x)  (ref_shim.cpp maps the kernels'
+ *     exp() to it; OpenCL only promises <= 3 ulp, glibc's expf is faithful but not correctly
+ *     rounded and has FMA / non-FMA variants, so it cannot serve as a portable definition)
  *   - scalar (float or double) * float3 converts the scalar to float first.
  * float3 occupies 16 bytes in __global memory exactly like OpenCL's float3.
  *

@@ -14,12 +14,17 @@ thread_local int lpcl_shim_gid = 0;
 #ifndef LPCL_REF_CL
 #error "build with -DLPCL_REF_CL=\"/abs/path/kernel_reflect_refract_intersect.cl\""
 #endif
+/* exp(float) inside the kernels (cl:391) is pinned as the correctly rounded float exponential:
+ * double exp rounded to float (see cl_shim.h).  The macro only affects the included .cl text. */
+static inline float lpcl_shim_exp(float x) { return (float)::exp((double)x); }
+#define exp(x) lpcl_shim_exp(x)
 #pragma GCC diagnostic push
 #pragma GCC diagnostic ignored "-Wunused-parameter"
 #pragma GCC diagnostic ignored "-Wunused-variable"
 #pragma GCC diagnostic ignored "-Wunused-value"
 #include LPCL_REF_CL
 #pragma GCC diagnostic pop
+#undef exp
 
 extern "C" {
 

@@ -312,7 +312,10 @@ static void material_one(int ray, const vec4f *origin, const vec4f *dest, const 
         if (mat_type[m1] == 0 && diss[m1] > tiny) { /* cl:389-393 */
             vec4f seg = v_sub(at, origin[ray]);
             float len = sqrtf(v_dot(seg, seg));
-            p = p * expf(-diss[m1] * len);
+            /* exp() of a float: pinned as the CORRECTLY ROUNDED float exponential, evaluated as the
+             * double exp rounded to float (OpenCL only bounds exp to 3 ulp; glibc's expf is faithful,
+             * not correctly rounded, and differs between its FMA / non-FMA ifunc variants) */
+            p = p * (float)exp((double)(-diss[m1] * len));
             power[ray] = p;
         }
     }
