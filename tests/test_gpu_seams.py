@@ -291,3 +291,77 @@ def test_resolve_and_scatter_seams_on_random_inputs(seed):
         assert np.array_equal(got["measured"], m_ref)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("seed,scale", [(0, 1.0), (1, 300.0), (2, 0.05)])
+def test_search_on_adversarial_triangle_soup(seed, scale):
+    """The search (filter + exact re-evaluation + atomic merge) against the oracle on a random
+    triangle soup with rays aimed AT edges, vertices and centroids, origins lying on other
+    triangles (t ~ EPSILON), rays parallel to faces, reversed and non-unit directions, duplicated
+    triangles (exact t ties between triangle indices and between meshes) and degenerate triangles."""
+    rng = np.random.RandomState(7 + seed)
+    T, M, n = 4000, 5, 12000
+    v0 = rng.uniform(-10, 10, (T, 3)) * scale
+    e1 = rng.normal(size=(T, 3)) * rng.choice([0.02, 0.3, 2.0], size=(T, 1)) * scale
+    e2 = rng.normal(size=(T, 3)) * rng.choice([0.02, 0.3, 2.0], size=(T, 1)) * scale
+    v1, v2 = v0 + e1, v0 + e2
+    dup = rng.choice(T, 200, replace=False)           # exact duplicates => exact t ties
+    src = rng.choice(T, 200)
+    v0[dup], v1[dup], v2[dup] = v0[src], v1[src], v2[src]
+    deg = rng.choice(T, 50, replace=False)
+    v2[deg] = v1[deg]                                 # zero-area triangles
+    tri_mesh = np.sort(rng.randint(0, M, T)).astype(np.int32)
+    tri_mesh[:M] = np.arange(M)                       # every mesh non-empty, ascending
+    tri_mesh = np.sort(tri_mesh)
+
+    class Soup:
+        pass
+
+    sc = Soup()
+    pad = lambda a: np.ascontiguousarray(np.concatenate((a, np.zeros((len(a), 1))), axis=1), dtype=np.float32)
+    sc.v0, sc.v1, sc.v2, sc.tri_mesh = pad(v0), pad(v1), pad(v2), tri_mesh
+    sc.tri_count, sc.mesh_count = T, M
+    sc.mat_type = np.zeros(M, np.int32)
+    sc.ior = np.ones(M, np.float32)
+    sc.refl = np.ones(M, np.float32)
+    sc.diss = np.zeros(M, np.float32)
+
+    tgt = rng.randint(0, T, n)
+    kind = rng.randint(0, 6, n)
+    a, b, c = sc.v0[tgt, :3].astype(np.float64), sc.v1[tgt, :3].astype(np.float64), sc.v2[tgt, :3].astype(np.float64)
+    u = rng.rand(n, 1)
+    point = np.where(kind[:, None] == 0, a + u * (b - a),                       # on edge v0-v1
+             np.where(kind[:, None] == 1, a + u * (c - a),                      # on edge v0-v2
+             np.where(kind[:, None] == 2, b + u * (c - b),                      # on edge v1-v2
+             np.where(kind[:, None] == 3, a, (a + b + c) / 3.0))))              # vertex / centroid
+    origin3 = rng.uniform(-12, 12, (n, 3)) * scale
+    on_tri = rng.rand(n) < 0.25                                                  # start ON another triangle
+    other = rng.randint(0, T, n)
+    w = rng.dirichlet([1, 1, 1], n)
+    origin3[on_tri] = (w[:, :1] * sc.v0[other, :3] + w[:, 1:2] * sc.v1[other, :3] + w[:, 2:] * sc.v2[other, :3])[on_tri]
+    d3 = point - origin3
+    par = kind == 5                                                              # parallel to the target's plane
+    d3[par] = (b - a)[par] + 0.3 * (c - a)[par]
+    norm = np.linalg.norm(d3, axis=1, keepdims=True)
+    norm[norm == 0] = 1.0
+    d3 = d3 / norm * rng.choice([1.0, 1.0, 1.0, -1.0, 0.01, 37.0], size=(n, 1))
+    origin = pad(origin3)
+    direc = pad(d3)
+    max_ray_len = np.float32(60.0 * scale)
+
+    want = oracle.intersect(sc, origin, direc, max_ray_len, "port")
+    g = GpuSeams(sc)
+    try:
+        for R, chunks in ((0, 0), (4, 5), (1, 3)):
+            if R:
+                os.environ["LPCL_SEARCH_R"], os.environ["LPCL_SEARCH_CHUNKS"] = str(R), str(chunks)
+            try:
+                got = g.intersect(origin, direc, max_ray_len)
+            finally:
+                os.environ.pop("LPCL_SEARCH_R", None), os.environ.pop("LPCL_SEARCH_CHUNKS", None)
+            assert np.array_equal(got[1], want[1]), "crossing counts differ (R=%d)" % R
+            assert np.array_equal(got[2], want[2]), "nearest triangle differs (R=%d)" % R
+            assert np.array_equal(util.bits(got[0]), util.bits(want[0])), "nearest t differs (R=%d)" % R
+    finally:
+        g.close()
+    assert (want[1] > 0).mean() > 0.3 and (want[1] > 1).sum() > 100  # the soup really is hit, often more than once
