@@ -16,8 +16,9 @@
 //     cycles (register-bank bandwidth), so the scalar formulation tops out near 55% of the FMA
 //     peak; FFMA2 with the triangle pair held in the operand-reuse cache across the R rays of a
 //     thread reads one even + two odd registers and runs at the full lane rate with half the issue
-//     slots.  The filter is two sign-agnostic products (lpcl_math.cuh): 20 FMA-pipe lane-ops
-//     + 1.5 ALU ops per test;
+//     slots.  The filter is two sign-agnostic products (lpcl_math.cuh): 19.25 FMA-pipe lane-ops
+//     + 1 ALU op ((a|b)&c on the sign bits) per test; measured 1.45e12 tests/s per B200 with the
+//     FMA pipe 77 % busy (profiles/);
 //   * only the rare candidates (a few per ray per sweep) take the exact, reference-ordered
 //     evaluation that decides the result;
 //   * per (ray, mesh) results (nearest t + triangle packed into one 64-bit key, crossing count)
