@@ -352,6 +352,9 @@ def main_native(args):
                            "FMA-pipe bound, neither HBM nor tensor (SURVEY.md 8(d)); MEASURED_PEAKS.json has no "
                            "FP32 entry" % (sm_count, sm_max_mhz),
             "algorithmic_flop_per_test": FLOP_PER_TEST, "launches": n_search,
+            "note": "frac uses the reference formulation's 52 FLOP/test (SURVEY.md 8(d)); the kernel executes "
+                    "19.25 FMA-pipe lane-ops (packed FFMA2) + 1 ALU op per test, so frac can exceed 1; ncu "
+                    "sm__pipe_fma_cycles_active = 77% (profiles/r1_search_kernel_0_ncu.txt)",
             "avg_launch_ms": search_ms / max(n_search, 1),
             "tests_per_s_kernel": (rays_total * tri) / (search_ms * 1e-3) if search_ms else 0.0,
             "share_of_step": search_ms / sum(step_ms) if step_ms else None,

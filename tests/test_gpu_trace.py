@@ -173,3 +173,19 @@ def test_edge_cases_single_ray_all_miss_and_tiny_scene():
     d = np.tile(np.array([[0, 0, 1, 0]], np.float32), (4, 1))
     graze = util.ArraySource(o, d, np.ones(4, np.float32))
     _check("grazing", [graze], [plate, box], params)
+
+
+def test_single_iteration_keeps_the_sources_power_shape():
+    """Reference quirk (it:404-409): with a single iteration get_measured_rays returns
+    the power in the source's shape, (K,1) for random_rays; later iterations flatten it."""
+    from lightpycl_b200 import geo_optical_elements as goe, light_source as lsm
+
+    np.random.seed(3)
+    src = lsm.light_source(power=1000.0, ray_count=2000)
+    dome = goe.optical_elements().hemisphere(center=[0, 0, 0, 0], radius=500.0)
+    dome.setMaterial(mat_type="measure")
+    params = dict(trace_iterations=4, trace_until_dissipated=0.99, max_ray_len=np.float32(1e3), ior_env=np.float32(1.0))
+    tr, ref = _check("bare source", [src], [dome], params)
+    pos, pwr = tr.get_measured_rays()
+    assert len(tr.results) == 1 and np.asarray(pwr).ndim == 2 and np.asarray(pwr).shape[1] == 1
+    assert abs(float(np.sum(np.asarray(pwr, np.float64))) - 1000.0) < 1.0  # energy conservation (ex_sph:105-109)
