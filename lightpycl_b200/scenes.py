@@ -204,7 +204,14 @@ def dissipative_cube(ray_count=10_000, trace_iterations=16, ior=1.0, dissipation
     return [src], [dome, block], params
 
 
+def lenslet_array_per_mesh(ray_count=1_000_000, **kw):
+    """C5' - the lenslet array with every lenslet its own mesh (mesh_count = 66): stresses the
+    per-(ray, mesh) search scratch and the generic (M > 8) media-resolution path."""
+    return lenslet_array(ray_count=ray_count, per_lenslet_mesh=True, **kw)
+
+
 CONFIGS = {
+    "c5p_lenslet_array_66_meshes": lenslet_array_per_mesh,
     "c1_nested_cubes": nested_cubes,
     "c2_directivity_lens": directivity_lens,
     "c3_parabolic_mirror": parabolic_mirror,
