@@ -434,12 +434,11 @@ extern "C" int lpcl_trace_resolve(const lpcl_scene *s, const lpcl_generation *pa
     char *scan = ws + lpcl_scratch_bytes(s, n);
     const int64_t scan_bytes = align_up(step_blocks(n) * 16 + 16, 256);
     CUDA_TRY(cudaMemsetAsync(scan, 0, (size_t)scan_bytes, stream));
-    unsigned *ticket = (unsigned *)scan;
-    unsigned long long *words = (unsigned long long *)(scan + 16);
+    unsigned long long *words = (unsigned long long *)(scan + 16); // two look-back status words per block
     step_kernel<<<(unsigned)step_blocks(n), STEP_THREADS, 0, stream>>>(
         s->dev, par, chi, key, cnt, (float4 *)d_dest_meas, (int4 *)d_hit, (float4 *)d_measured_out,
         (unsigned long long *)d_measured_lineage, measured_base, measured_capacity, (StepCounters *)d_counters, words,
-        ticket, max_ray_len, ior_env, iteration);
+        max_ray_len, ior_env, iteration);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
