@@ -11,6 +11,7 @@
 
 #include "../../include/lightpycl_b200.h"
 #include "lpcl_material.cuh"
+#include "lpcl_search_tc.cuh"
 
 using namespace lpcl;
 
@@ -46,6 +47,15 @@ static const SearchVariant kVariants[] = {
 static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 static const int kDefaultVariant = 4;
 
+// tensor-core search: ray tiles (128 rays each) per CTA
+struct TcVariant {
+    int rt;
+    SearchFn fn;
+};
+static const TcVariant kTcVariants[] = {
+    {1, search_tc_kernel<1>}, {2, search_tc_kernel<2>}, {4, search_tc_kernel<4>}, {8, search_tc_kernel<8>}};
+static const int kNumTcVariants = (int)(sizeof(kTcVariants) / sizeof(kTcVariants[0]));
+
 struct lpcl_scene {
     SceneDev dev;
     int occupancy[8] = {1, 1, 1, 1, 1, 1, 1, 1};
@@ -67,7 +77,9 @@ static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static int64_t scene_bytes_bound(int64_t tri_count, int64_t mesh_count)
 {
     const int64_t max_tiles = (tri_count + TILE_TRIS - 1) / TILE_TRIS + mesh_count;
+    const int64_t max_tc_tiles = (tri_count + TC_TILE_TRIS - 1) / TC_TILE_TRIS + mesh_count;
     return align_up(max_tiles * TILE_BYTES, 256) + align_up(max_tiles * (int64_t)sizeof(TileInfo), 256) +
+           align_up(max_tc_tiles * TC_TILE_BYTES, 256) + align_up(max_tc_tiles * (int64_t)sizeof(TileInfo), 256) +
            4 * align_up(mesh_count * 4, 256) + 256;
 }
 
@@ -90,7 +102,7 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     cudaStream_t stream = (cudaStream_t)stream_;
 
     // tile table: contiguous ascending mesh ids, every mesh non-empty (reference relies on it, cl:262-265)
-    std::vector<TileInfo> tiles;
+    std::vector<TileInfo> tiles, tc_tiles;
     int expect = 0;
     if (h_tri_mesh[0] != 0) return fail(LPCL_E_MESH_IDS, "mesh ids must start at 0 (got %d)", h_tri_mesh[0]);
     int start = 0;
@@ -106,6 +118,14 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
                 ti.mesh = expect;
                 ti.pad = 0;
                 tiles.push_back(ti);
+            }
+            for (int t0 = start; t0 < i; t0 += TC_TILE_TRIS) {
+                TileInfo ti;
+                ti.tri0 = t0;
+                ti.count = (i - t0 < TC_TILE_TRIS) ? (i - t0) : TC_TILE_TRIS;
+                ti.mesh = expect;
+                ti.pad = 0;
+                tc_tiles.push_back(ti);
             }
             start = i;
             ++expect;
@@ -126,7 +146,10 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     const int64_t off_refl = off_ior + align_up((int64_t)mesh_count * 4, 256);
     const int64_t off_diss = off_refl + align_up((int64_t)mesh_count * 4, 256);
     const int64_t off_vmax = off_diss + align_up((int64_t)mesh_count * 4, 256);
-    const int64_t total = off_vmax + 256;
+    const int tc_n_tiles = (int)tc_tiles.size();
+    const int64_t off_tc_filter = off_vmax + 256;
+    const int64_t off_tc_tiles = align_up(off_tc_filter + (int64_t)tc_n_tiles * TC_TILE_BYTES, 256);
+    const int64_t total = align_up(off_tc_tiles + (int64_t)tc_n_tiles * sizeof(TileInfo), 256);
     char *base = nullptr;
     if (borrow) { // caller-owned memory (e.g. a torch tensor): no cudaMalloc / cudaFree on this path
         if (!d_mem || mem_bytes < total || (reinterpret_cast<uintptr_t>(d_mem) & 255u)) {
@@ -156,6 +179,9 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     d.refl = (const float *)(base + off_refl);
     d.diss = (const float *)(base + off_diss);
     d.vmax = (const float *)(base + off_vmax);
+    d.tc_filter = (const float *)(base + off_tc_filter);
+    d.tc_tiles = (const TileInfo *)(base + off_tc_tiles);
+    d.tc_n_tiles = tc_n_tiles;
     d.n_tiles = n_tiles;
     d.tri_count = tri_count;
     d.mesh_count = mesh_count;
@@ -171,6 +197,7 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     } while (0)
     // small host->device copies; the sources are pageable so these complete before returning
     SCENE_TRY(cudaMemcpyAsync(base + off_tiles, tiles.data(), n_tiles * sizeof(TileInfo), cudaMemcpyHostToDevice, stream));
+    SCENE_TRY(cudaMemcpyAsync(base + off_tc_tiles, tc_tiles.data(), tc_n_tiles * sizeof(TileInfo), cudaMemcpyHostToDevice, stream));
     SCENE_TRY(cudaMemcpyAsync(base + off_mat, h_mat_type, mesh_count * 4, cudaMemcpyHostToDevice, stream));
     SCENE_TRY(cudaMemcpyAsync(base + off_ior, h_ior, mesh_count * 4, cudaMemcpyHostToDevice, stream));
     SCENE_TRY(cudaMemcpyAsync(base + off_refl, h_refl, mesh_count * 4, cudaMemcpyHostToDevice, stream));
@@ -182,7 +209,13 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     const long long slots = (long long)n_tiles * TILE_TRIS;
     build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles, d.vmax,
                                                                             (float4 *)(base + off_filter));
+    const long long tc_slots = (long long)tc_n_tiles * TC_TILE_TRIS;
+    build_tc_kernel<<<(unsigned)((tc_slots + 127) / 128), 128, 0, stream>>>(d.v0, d.v1, d.v2, d.tc_tiles, tc_n_tiles, d.vmax,
+                                                                           (float *)(base + off_tc_filter));
     SCENE_TRY(cudaGetLastError());
+    for (int v = 0; v < kNumTcVariants; ++v)
+        SCENE_TRY(cudaFuncSetAttribute(kTcVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tc_smem_bytes(kTcVariants[v].rt)));
     for (int v = 0; v < kNumVariants; ++v) {
         SCENE_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
         int occ = 0;
@@ -261,6 +294,32 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         long long blocks = (total + 255) / 256;
         if (blocks > (long long)s->sm_count * 32) blocks = (long long)s->sm_count * 32;
         scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key);
+    }
+    // LPCL_SEARCH_IMPL=tc: filter on the tensor cores (lpcl_search_tc.cuh); simt: packed-FP32 filter
+    const char *impl = getenv("LPCL_SEARCH_IMPL");
+    if (impl && !strcmp(impl, "tc")) {
+        const int want_rt = env_int("LPCL_SEARCH_RT", 0);
+        int v = -1;
+        for (int k = 0; k < kNumTcVariants; ++k)
+            if (kTcVariants[k].rt == want_rt) v = k;
+        if (v < 0) {
+            v = kNumTcVariants - 1;
+            while (v > 0 && n < 8LL * kTcVariants[v].rt * TC_M) --v;
+        }
+        const int64_t per_cta = (int64_t)kTcVariants[v].rt * TC_M;
+        const int64_t ray_blocks = (n + per_cta - 1) / per_cta;
+        int64_t chunks = env_int("LPCL_SEARCH_CHUNKS", 0);
+        if (chunks <= 0) chunks = (8 * (int64_t)s->sm_count + ray_blocks - 1) / ray_blocks; // one CTA per SM
+        if (chunks < 1) chunks = 1;
+        if (chunks > s->dev.tc_n_tiles) chunks = s->dev.tc_n_tiles;
+        if (chunks > 65535) chunks = 65535;
+        int tiles_per_chunk = (int)((s->dev.tc_n_tiles + chunks - 1) / chunks);
+        chunks = (s->dev.tc_n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
+        kTcVariants[v].fn<<<grid, TC_THREADS, tc_smem_bytes(kTcVariants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
+                                                                                          tiles_per_chunk, cand_total);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
     // variant: forced by the environment (tests / tuning), else the default, stepping down to fewer
     // rays per CTA while the last ray block would be mostly padding

@@ -194,6 +194,98 @@ LPCL_HD bool filter_candidate(const FilterRec &q, float dx, float dy, float dz, 
 }
 
 // ------------------------------------------------------------------------------------------
+// The same filter evaluated by the tensor cores (lpcl_search_tc.cuh).
+//
+// DEN, uN and vN are linear in the ray's six numbers (M, D), so a tile of rays x a tile of
+// triangles is a GEMM with K = 6: D[ray][3 t + {0,1,2}] = (M, D)_ray . row_{t,{DEN,uN,vN}}.  The
+// tensor cores multiply TF32 (11-bit significands), so every fp32 operand x is split into
+// x = hi + lo (+ <= 2^-22 |x|), hi = tf32(x), lo = tf32(x - hi), and the four partial products
+// hi.hi + hi.lo + lo.hi + lo.lo are laid along K (4 x 6 = 24 = three kind::tf32 MMAs of K = 8).
+// Each triangle's three rows are pre-scaled by s = 1/sqrt(G2tc_tri), which turns the margin
+// m = K2_ray * G2tc_tri into the per-RAY constant K2_ray:
+//   candidate  <=>  uN' (DEN' - uN') + K2_ray >= 0  and  vN' (DEN' - vN') + K2_ray >= 0.
+//
+// Margin.  Measured on B200 (tools/ubench_tmem.cu, profiles/r1_ubench_tmem.txt): a kind::tf32
+// tcgen05.mma sums its K = 8 products and the accumulator with extra bits and truncates once
+// (|err| <= 2.7 u sum|terms| observed per instruction, 6.2 u over three); budget 16 u.  Operand
+// splitting costs <= 4 u per operand, M = O x D in fp32 <= 2 u, the scaled coefficient's
+// rounding <= 1 u: eps_filter <= (16 + 6 + 5) u |D| Emax (|O| + |V0|), plus the reference's own
+// 7 u, times the same 1.5 allowance: eps = 56 u |D| Emax L.  The bound of the fp32 filter above
+// with this eps reads  -(4 u d^2 + 3 eps |d| + 2 eps^2) >= -u |D|^2 Emax L (172 E12 + 6272 u Emax L),
+// so G2tc_tri = Emax (172 E12 + 6272 u Emax Lcap) with the same K2_ray.
+LPCL_HD float tf32_rna(float x) // round to nearest (ties away) to 10 explicit mantissa bits, as cvt.rna.tf32.f32
+{
+    union { float f; uint32_t u; } v;
+    v.f = x;
+    v.u = (v.u + 0x1000u) & 0xffffe000u;
+    return v.f;
+}
+LPCL_HD void tf32_split(float x, float &hi, float &lo)
+{
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi); // x - hi is exact in binary32
+}
+
+struct TcRows {
+    float c[3][6]; // rows DEN', uN', vN' over (Mx, My, Mz, Dx, Dy, Dz)
+};
+
+LPCL_HD TcRows make_tc_rows(V3 v0, V3 v1, V3 v2, float vmax)
+{
+    V3 e1 = sub(v1, v0), e2 = sub(v2, v0);
+    double e1x = e1.x, e1y = e1.y, e1z = e1.z, e2x = e2.x, e2y = e2.y, e2z = e2.z;
+    double ox = v0.x, oy = v0.y, oz = v0.z;
+    double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
+    double emax = l1 > l2 ? l1 : l2;
+    double g = emax * (172.0 * l1 * l2 + 3.74e-4 * emax * 4.0 * (double)vmax) * 1.001; // 6272 * 2^-24 = 3.738e-4
+    double s = 1.0 / sqrt(g > 1e-30 ? g : 1e-30);
+    TcRows r;
+    r.c[0][0] = r.c[0][1] = r.c[0][2] = 0.0f;
+    r.c[0][3] = (float)(s * (e2y * e1z - e2z * e1y)); // Nn
+    r.c[0][4] = (float)(s * (e2z * e1x - e2x * e1z));
+    r.c[0][5] = (float)(s * (e2x * e1y - e2y * e1x));
+    r.c[1][0] = (float)(s * e2x);                     // E2
+    r.c[1][1] = (float)(s * e2y);
+    r.c[1][2] = (float)(s * e2z);
+    r.c[1][3] = (float)(s * (oy * e2z - oz * e2y));   // A = V0 x E2
+    r.c[1][4] = (float)(s * (oz * e2x - ox * e2z));
+    r.c[1][5] = (float)(s * (ox * e2y - oy * e2x));
+    r.c[2][0] = (float)(-s * e1x);                    // E1n
+    r.c[2][1] = (float)(-s * e1y);
+    r.c[2][2] = (float)(-s * e1z);
+    r.c[2][3] = (float)(s * (e1y * oz - e1z * oy));   // B = E1 x V0
+    r.c[2][4] = (float)(s * (e1z * ox - e1x * oz));
+    r.c[2][5] = (float)(s * (e1x * oy - e1y * ox));
+    return r;
+}
+
+// Host model of the tensor-core filter for the property test: the three GEMM outputs are formed
+// exactly from the split operands (double), then pushed by +-16 u sum|terms| in the direction
+// `push` selects (bit 0: DEN', bit 1: uN', bit 2: vN'); the caller requires a reference hit to be a
+// candidate for every push.  Not used on the GPU.
+LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, float mx, float my, float mz, float k2, int push)
+{
+    const float a[6] = {mx, my, mz, dx, dy, dz};
+    float out[3];
+    for (int r = 0; r < 3; ++r) {
+        double s = 0.0, sabs = 0.0;
+        for (int k = 0; k < 6; ++k) {
+            float ah, al, bh, bl;
+            tf32_split(a[k], ah, al);
+            tf32_split(q.c[r][k], bh, bl);
+            double p = ((double)ah + (double)al) * ((double)bh + (double)bl);
+            s += p;
+            sabs += p < 0 ? -p : p;
+        }
+        const double e = 16.0 * 5.9604644775390625e-8 * sabs;
+        out[r] = (float)(s + (((push >> r) & 1) ? e : -e));
+    }
+    const float pu = LPCL_FMA(out[1], LPCL_SUB(out[0], out[1]), k2);
+    const float pv = LPCL_FMA(out[2], LPCL_SUB(out[0], out[2]), k2);
+    return !(signbit(pu) || signbit(pv));
+}
+
+// ------------------------------------------------------------------------------------------
 // Per-ray resolution of the per-mesh search results, cl:105-240.
 struct Resolve {
     float t;                 // distance to the end point

@@ -59,7 +59,9 @@ struct SceneDev {
     const int *mat_type;          // mesh_count
     const float *ior, *refl, *diss;
     const float *vmax;            // device scalar: max vertex norm
-    int n_tiles, tri_count, mesh_count;
+    const float *tc_filter;       // tc_n_tiles * TC_TILE_FLOATS (lpcl_search_tc.cuh)
+    const TileInfo *tc_tiles;     // tc_n_tiles
+    int n_tiles, tri_count, mesh_count, tc_n_tiles;
 };
 
 // A ray generation stored in two segments (see include/lightpycl_b200.h).

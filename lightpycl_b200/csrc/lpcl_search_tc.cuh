@@ -1,0 +1,387 @@
+// lpcl_search_tc.cuh - the nearest-hit search with its filter on the 5th-generation tensor cores.
+//
+// Same contract as search_kernel (lpcl_search.cuh; reference `intersect`, cl:243-289): per
+// (ray, mesh) the nearest accepted t + triangle and the crossing count, merged with atomicMin /
+// atomicAdd into the mesh-major scratch.  What changes is who evaluates the conservative filter
+// (lpcl_math.cuh, "the same filter evaluated by the tensor cores"):
+//
+//   D[128 rays][192] = A[128 rays][K = 24] . B[64 triangles x {DEN', uN', vN'}][K = 24]^T
+//
+// is three kind::tf32 tcgen05.mma (M = 128, N = 192, K = 8) per (ray tile, triangle tile); the 24
+// K-slots carry the four partial products of the hi/lo TF32 split of the six ray numbers (M, D)
+// and of the triangle's scaled coefficients.  The accumulator lives in TMEM (two 192-column
+// buffers, so the MMAs of the next ray tile overlap the epilogue of this one); the epilogue warps
+// read it back with tcgen05.ld (lane = ray, 6 consecutive columns = one pair of triangles), apply
+// the two sign-agnostic product tests with packed FP32 (2 x sub.f32x2 + 2 x fma.rn.f32x2 + 2 x LOP3
+// per PAIR of triangles - the 15 FMAs per test of the SIMT kernel are gone) and hand the rare
+// candidates to the exact, reference-ordered evaluation, which alone decides results.
+//
+// CTA = 10 warps, one CTA per SM:
+//   warps 0-7  epilogue; warp w reads TMEM lanes 32 (w % 4) .. +31 (its rays) and the triangle
+//              chunks of half w / 4; they also stage the A operand (RT ray tiles) once per CTA;
+//   warp 8     TMA producer: one bulk copy (18 KB) per triangle tile, TC_STAGES deep;
+//   warp 9     MMA issuer (one lane): waits tile + free accumulator, issues 3 MMAs, commits.
+// Shared-memory operands use the no-swizzle K-major canonical layout (8-row x 16-byte core
+// matrices): element (row, k) at (k / 4) * rows * 16 + (row / 8) * 128 + (row % 8) * 16 + (k % 4) * 4.
+// The triangle tiles are stored in exactly that layout in global memory, so a tile is one 1-D TMA
+// bulk copy.  Measured pieces (tools/ubench_tmem.cu): tcgen05.ld sustains > 400 B/clk/SM, a
+// 128x256x8 tf32 MMA issues every 167 clk.
+#pragma once
+
+#include "lpcl_search.cuh"
+
+namespace lpcl {
+
+constexpr int TC_TILE_TRIS = 64;                       // triangles per B tile
+constexpr int TC_N = 3 * TC_TILE_TRIS;                 // 192 accumulator columns
+constexpr int TC_K = 24;                               // 4 partial products x 6
+constexpr int TC_M = 128;                              // rays per A tile (= TMEM lanes)
+constexpr int TC_TILE_FLOATS = TC_N * TC_K;            // 4608
+constexpr int TC_TILE_BYTES = TC_TILE_FLOATS * 4;      // 18432
+constexpr int TC_A_FLOATS = TC_M * TC_K;               // 3072
+constexpr int TC_A_BYTES = TC_A_FLOATS * 4;            // 12288
+constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_PRODUCER_WARP = 8;
+constexpr int TC_MMA_WARP = 9;
+constexpr int TC_THREADS = 320;
+constexpr int TC_CHUNK_TRIS = 16;                      // triangles per epilogue chunk (48 columns)
+constexpr int TC_ACC_STRIDE = 256;                     // TMEM columns between the two accumulators
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__host__ __device__ inline int tc_canon(int row, int k, int rows) // float index inside an operand tile
+{
+    return (k >> 2) * rows * 4 + (row >> 3) * 32 + (row & 7) * 4 + (k & 3);
+}
+// dynamic shared memory of the kernel: padded past half an SM so that two CTAs (two 512-column
+// TMEM allocations) never share an SM
+__host__ __device__ constexpr int tc_smem_bytes(int rt)
+{
+    return (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + 256) > 120 * 1024 ? (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + 256)
+                                                                            : 120 * 1024;
+}
+
+// ------------------------------------------------------------------------------------------ scene build
+// one thread per (tile, triangle slot): three rows of 24 floats scattered into the canonical layout
+__global__ void build_tc_kernel(const float4 *v0, const float4 *v1, const float4 *v2, const TileInfo *tiles, int n_tiles,
+                                const float *vmax, float *out)
+{
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= (long long)n_tiles * TC_TILE_TRIS) return;
+    const int tile = (int)(slot / TC_TILE_TRIS), j = (int)(slot % TC_TILE_TRIS);
+    const TileInfo ti = tiles[tile];
+    float *dst = out + (long long)tile * TC_TILE_FLOATS;
+    TcRows r;
+    if (j < ti.count) {
+        float4 a = v0[ti.tri0 + j], b = v1[ti.tri0 + j], c = v2[ti.tri0 + j];
+        r = make_tc_rows(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), *vmax);
+    } else { // padding: never read back (the epilogue stops at ti.count)
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 6; ++k) r.c[q][k] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int row = 6 * (j >> 1) + 2 * q + (j & 1); // pair-interleaved: DEN'(2p,2p+1) uN'(..) vN'(..)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float hi, lo;
+            tf32_split(r.c[q][k], hi, lo);
+            dst[tc_canon(row, k, TC_N)] = hi;       // x A_hi
+            dst[tc_canon(row, 6 + k, TC_N)] = lo;   // x A_hi
+            dst[tc_canon(row, 12 + k, TC_N)] = hi;  // x A_lo
+            dst[tc_canon(row, 18 + k, TC_N)] = lo;  // x A_lo
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tcgen05 PTX
+__device__ __forceinline__ void tc_alloc_512(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_free_512(uint32_t addr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory matrix descriptor: no swizzle, K-major; LBO = bytes between the two 16-byte K halves
+// of one MMA, SBO = bytes between 8-row groups
+__device__ __forceinline__ uint64_t tc_smem_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes)
+{
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+                 : "memory");
+}
+// arrives on the mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#define LPCL_R8(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+// 48 consecutive accumulator columns of this thread's TMEM lane (SASS: LDTM.x32 + LDTM.x16)
+__device__ __forceinline__ void tc_ld_48(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : LPCL_R8(r, 0), LPCL_R8(r, 8), LPCL_R8(r, 16), LPCL_R8(r, 24)
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : LPCL_R8(r, 32), LPCL_R8(r, 40)
+                 : "r"(taddr + 32u)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ exact path
+struct CandResult {
+    float t;   // nearest accepted t among the candidates (max_ray_len if none)
+    int tri;   // its triangle (-1 if none)
+    int hits;  // accepted candidates
+};
+// mask bit b = triangle tri_base + b passed the filter; evaluated in ascending triangle order with
+// a strict < so that the first index wins ties (cl:278)
+__device__ __noinline__ CandResult tc_candidates(unsigned mask, int tri_base, int tri_end, const float4 *tv0, const float4 *tv1,
+                                                 const float4 *tv2, const float4 *org_pow, const float4 *dir_prev,
+                                                 long long phys, float eps, float t_init)
+{
+    CandResult res;
+    res.t = t_init;
+    res.tri = -1;
+    res.hits = 0;
+    const float4 o = org_pow[phys], d = dir_prev[phys];
+    while (mask) {
+        const int b = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        const int tri = tri_base + b;
+        if (tri >= tri_end) break;
+        const float4 a = __ldg(tv0 + tri), bb = __ldg(tv1 + tri), c = __ldg(tv2 + tri);
+        float t;
+        if (ray_triangle_exact(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z),
+                               v3(c.x, c.y, c.z), t) &&
+            t > eps) {
+            res.hits += 1;
+            if (t < res.t) {
+                res.t = t;
+                res.tri = tri;
+            }
+        }
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------ the sweep
+template <int RT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *__restrict__ key, int *__restrict__ cnt,
+                 int tiles_per_chunk, unsigned long long *cand_total)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *b_buf = reinterpret_cast<float *>(smem_raw);
+    float *a_buf = reinterpret_cast<float *>(smem_raw + TC_STAGES * TC_TILE_BYTES);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + TC_STAGES * TC_TILE_BYTES + RT * TC_A_BYTES);
+    uint64_t *empty_bar = full_bar + TC_STAGES;
+    uint64_t *tfull_bar = empty_bar + TC_STAGES; // [2] accumulator ready   (MMA commit -> epilogue)
+    uint64_t *tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA issuer)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.y * tiles_per_chunk;
+    const int c1 = min(c0 + tiles_per_chunk, sc.tc_n_tiles);
+    const int nt = max(c1 - c0, 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC_MMA_WARP) tc_alloc_512(tmem_slot);
+
+    // epilogue threads: per-ray state, and the A operand (each ray row written by one of its two threads)
+    const int row = (warp & 3) * 32 + lane; // TMEM lane == ray row of every ray tile
+    const int half = (warp >> 2) & 1;
+    const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
+    const float eps = eps_len(max_ray_len);
+    float tmin[RT];
+    int best[RT], hits[RT];
+    u64 k2[RT];
+    if (warp < TC_EPI_WARPS) {
+        const float vmax = *sc.vmax;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+            // a row beyond the last ray sweeps a copy of the last ray (never flushed)
+            const long long i = min(ray0 + (long long)j * TC_M, rays.n - 1);
+            const long long ph = rays.phys(i);
+            const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
+            const float kk = filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax);
+            k2[j] = pack2(__float_as_uint(kk), __float_as_uint(kk));
+            tmin[j] = max_ray_len;
+            best[j] = -1;
+            hits[j] = 0;
+            if ((j & 1) == half) {
+                const float a6[6] = {o.y * d.z - o.z * d.y, o.z * d.x - o.x * d.z, o.x * d.y - o.y * d.x, d.x, d.y, d.z};
+                float *dst = a_buf + j * TC_A_FLOATS;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    float hi, lo;
+                    tf32_split(a6[k], hi, lo);
+                    dst[tc_canon(row, k, TC_M)] = hi;       // x B_hi
+                    dst[tc_canon(row, 6 + k, TC_M)] = hi;   // x B_lo
+                    dst[tc_canon(row, 12 + k, TC_M)] = lo;  // x B_hi
+                    dst[tc_canon(row, 18 + k, TC_M)] = lo;  // x B_lo
+                }
+            }
+        }
+    }
+    fence_async_smem(); // generic-proxy writes of A -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TC_PRODUCER_WARP) {
+        if (lane == 0) {
+            for (int it = 0; it < nt; ++it) {
+                const int s = it % TC_STAGES;
+                if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (unsigned)((it / TC_STAGES - 1) & 1));
+                mbar_arrive_expect_tx(&full_bar[s], TC_TILE_BYTES);
+                tma_load_bulk(b_buf + s * TC_TILE_FLOATS, sc.tc_filter + (long long)(c0 + it) * TC_TILE_FLOATS, TC_TILE_BYTES,
+                              &full_bar[s]);
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        if (lane == 0) {
+            const unsigned a_addr = smem_u32(a_buf), b_addr = smem_u32(b_buf);
+            for (int it = 0; it < nt; ++it) {
+                const int s = it % TC_STAGES;
+                mbar_wait(&full_bar[s], (unsigned)((it / TC_STAGES) & 1));
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < RT; ++j) {
+                    const int g = it * RT + j, buf = g & 1, use = g >> 1;
+                    if (use > 0) mbar_wait(&tempty_bar[buf], (unsigned)((use - 1) & 1));
+                    tc_fence_after();
+                    const uint32_t acc = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint64_t da = tc_smem_desc(a_addr + j * TC_A_BYTES + ks * 2 * TC_M * 16, TC_M * 16, 128);
+                        const uint64_t db = tc_smem_desc(b_addr + s * TC_TILE_BYTES + ks * 2 * TC_N * 16, TC_N * 16, 128);
+                        tc_mma_tf32(acc, da, db, ks > 0 ? 1u : 0u);
+                    }
+                    tc_commit(&tfull_bar[buf]);
+                }
+                tc_commit(&empty_bar[s]); // the tile's shared-memory slot is free once its MMAs have completed
+            }
+        }
+    } else {
+        unsigned n_cand = 0;
+        auto flush = [&](int mesh) {
+#pragma unroll
+            for (int j = 0; j < RT; ++j) {
+                const long long i = ray0 + (long long)j * TC_M;
+                if (i < rays.n) {
+                    const long long slot = (long long)mesh * rays.n + i;
+                    if (hits[j]) atomicAdd(&cnt[slot], hits[j]);
+                    if (best[j] >= 0) atomicMin(&key[slot], pack_key(tmin[j], best[j]));
+                }
+                tmin[j] = max_ray_len;
+                best[j] = -1;
+                hits[j] = 0;
+            }
+        };
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int cur_mesh = -1;
+        for (int it = 0; it < nt; ++it) {
+            const int4 ti4 = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it));
+            const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
+            if (mesh != cur_mesh) {
+                if (cur_mesh >= 0) flush(cur_mesh);
+                cur_mesh = mesh;
+            }
+#pragma unroll
+            for (int j = 0; j < RT; ++j) {
+                const int g = it * RT + j, buf = g & 1;
+                mbar_wait(&tfull_bar[buf], (unsigned)((g >> 1) & 1));
+                tc_fence_after();
+                const long long i = ray0 + (long long)j * TC_M;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int chunk = half * 2 + cc; // 16 triangles, 48 columns
+                    if (chunk * TC_CHUNK_TRIS < count) {
+                        uint32_t r[48];
+                        __syncwarp(); // reconverge after a divergent exact path: tcgen05.ld is warp-collective
+                        tc_ld_48(lane_addr + (uint32_t)(buf * TC_ACC_STRIDE + chunk * 48), r);
+                        tc_wait_ld();
+                        if (cc == 1 || (chunk + 1) * TC_CHUNK_TRIS >= count) { // last read of this accumulator by this warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                        }
+                        u64 pu[8], pv[8];
+                        unsigned none = 0xffffffffu; // sign bit survives only if every test of the chunk failed
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const u64 den = pack2(r[6 * q + 0], r[6 * q + 1]);
+                            const u64 un = pack2(r[6 * q + 2], r[6 * q + 3]);
+                            const u64 vn = pack2(r[6 * q + 4], r[6 * q + 5]);
+                            pu[q] = ffma2(un, fsub2(den, un), k2[j]); // uN' (DEN' - uN') + K2
+                            pv[q] = ffma2(vn, fsub2(den, vn), k2[j]); // vN' (DEN' - vN') + K2
+                            none = or_and(lo32(pu[q]), lo32(pv[q]), none);
+                            none = or_and(hi32(pu[q]), hi32(pv[q]), none);
+                        }
+                        if ((int)none >= 0) { // rare: some triangle of the chunk passed both tests for this ray
+                            unsigned mask = 0;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                mask |= ((~(lo32(pu[q]) | lo32(pv[q]))) >> 31) << (2 * q);
+                                mask |= ((~(hi32(pu[q]) | hi32(pv[q]))) >> 31) << (2 * q + 1);
+                            }
+                            n_cand += __popc(mask);
+                            if (i < rays.n) {
+                                const CandResult cr =
+                                    tc_candidates(mask, tri0 + chunk * TC_CHUNK_TRIS, tri0 + count, sc.v0, sc.v1, sc.v2,
+                                                  rays.org_pow, rays.dir_prev, rays.phys(i), eps, max_ray_len);
+                                hits[j] += cr.hits;
+                                if (cr.tri >= 0 && cr.t < tmin[j]) { // strict: earlier chunks hold lower triangle indices
+                                    tmin[j] = cr.t;
+                                    best[j] = cr.tri;
+                                }
+                            }
+                        }
+                    } else if (cc == 0) { // nothing to read in this accumulator for this warp: release it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                    }
+                }
+            }
+        }
+        if (cur_mesh >= 0) flush(cur_mesh);
+        if (cand_total) {
+            for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+            if (lane == 0 && n_cand) atomicAdd(cand_total, (unsigned long long)n_cand);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) tc_free_512(tmem_base);
+}
+
+} // namespace lpcl

@@ -15,8 +15,8 @@ static inline double rnd() { // xorshift64*
 }
 static inline double srnd() { return 2.0 * rnd() - 1.0; }
 
-extern "C" long filter_property(long n, unsigned seed, double scene_radius, double tri_size, double origin_radius,
-                                int unit_dirs, long *n_exact, long *n_cand, double *worst)
+static long property(int tc, long n, unsigned seed, double scene_radius, double tri_size, double origin_radius,
+                     int unit_dirs, long *n_exact, long *n_cand, double *worst)
 {
     s_state = 0x9E3779B97F4A7C15ULL ^ ((uint64_t)seed << 17);
     long violations = 0;
@@ -48,13 +48,32 @@ extern "C" long filter_property(long n, unsigned seed, double scene_radius, doub
         V3 d = v3((float)(dxd * sc), (float)(dyd * sc), (float)(dzd * sc));
         float t;
         bool hit = ray_triangle_exact(o, d, a, b, c, t);
-        FilterRec q = make_filter_rec(a, b, c, vmax);
         float mx = o.y * d.z - o.z * d.y, my = o.z * d.x - o.x * d.z, mz = o.x * d.y - o.y * d.x;
         float k2 = filter_ray_scale(o, d, vmax);
-        bool cand = filter_candidate(q, d.x, d.y, d.z, mx, my, mz, k2);
+        bool cand;
+        if (tc) { // tensor-core model: a candidate under every admissible rounding of the three GEMM outputs
+            TcRows q = make_tc_rows(a, b, c, vmax);
+            cand = true;
+            for (int push = 0; push < 8; ++push) cand = cand && filter_candidate_tc(q, d.x, d.y, d.z, mx, my, mz, k2, push);
+        } else {
+            FilterRec q = make_filter_rec(a, b, c, vmax);
+            cand = filter_candidate(q, d.x, d.y, d.z, mx, my, mz, k2);
+        }
         *n_exact += hit;
         *n_cand += cand;
         if (hit && !cand) ++violations;
     }
     return violations;
+}
+
+extern "C" long filter_property(long n, unsigned seed, double scene_radius, double tri_size, double origin_radius,
+                                int unit_dirs, long *n_exact, long *n_cand, double *worst)
+{
+    return property(0, n, seed, scene_radius, tri_size, origin_radius, unit_dirs, n_exact, n_cand, worst);
+}
+
+extern "C" long filter_property_tc(long n, unsigned seed, double scene_radius, double tri_size, double origin_radius,
+                                   int unit_dirs, long *n_exact, long *n_cand, double *worst)
+{
+    return property(1, n, seed, scene_radius, tri_size, origin_radius, unit_dirs, n_exact, n_cand, worst);
 }

@@ -154,9 +154,31 @@ def test_three_seams_match_oracle(name):
         g.close()
 
 
-@pytest.mark.parametrize("R,chunks", [(1, 1), (2, 1), (4, 1), (1, 7), (2, 3), (4, 64)])
-def test_search_variants_agree(R, chunks):
-    """Rays-per-thread variants and triangle-range splits (atomic merge) give identical results."""
+SEARCH_ENV = ("LPCL_SEARCH_IMPL", "LPCL_SEARCH_R", "LPCL_SEARCH_RT", "LPCL_SEARCH_CHUNKS")
+
+
+def _set_search(impl, R, chunks):
+    """impl 'simt': R rays per thread; impl 'tc': R ray tiles (128 rays) per CTA; 0 = heuristic."""
+    for k in SEARCH_ENV:
+        os.environ.pop(k, None)
+    os.environ["LPCL_SEARCH_IMPL"] = impl
+    if R:
+        os.environ["LPCL_SEARCH_RT" if impl == "tc" else "LPCL_SEARCH_R"] = str(R)
+    if chunks:
+        os.environ["LPCL_SEARCH_CHUNKS"] = str(chunks)
+
+
+def _clear_search():
+    for k in SEARCH_ENV:
+        os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("impl,R,chunks", [("simt", 1, 1), ("simt", 2, 1), ("simt", 4, 1), ("simt", 1, 7), ("simt", 2, 3),
+                                           ("simt", 4, 64), ("tc", 1, 1), ("tc", 2, 1), ("tc", 4, 3), ("tc", 8, 1),
+                                           ("tc", 1, 64), ("tc", 0, 0)])
+def test_search_variants_agree(impl, R, chunks):
+    """Both search kernels (packed-FP32 filter, tensor-core filter), their rays-per-CTA variants and
+    triangle-range splits (atomic merge) give results identical to the oracle's."""
     from lightpycl_b200 import scenes
 
     ls, meshes, params = scenes.directivity_lens(ray_count=5000)
@@ -164,11 +186,11 @@ def test_search_variants_agree(R, chunks):
     origin, direc, _, _ = oracle.flatten_sources(ls)
     want = oracle.intersect(sc, origin, direc, params["max_ray_len"], "port")
     g = GpuSeams(sc)
-    os.environ["LPCL_SEARCH_R"], os.environ["LPCL_SEARCH_CHUNKS"] = str(R), str(chunks)
+    _set_search(impl, R, chunks)
     try:
         got = g.intersect(origin, direc, np.float32(params["max_ray_len"]))
     finally:
-        os.environ.pop("LPCL_SEARCH_R"), os.environ.pop("LPCL_SEARCH_CHUNKS")
+        _clear_search()
         g.close()
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
     assert np.array_equal(util.bits(got[0]), util.bits(want[0]))
@@ -352,16 +374,15 @@ def test_search_on_adversarial_triangle_soup(seed, scale):
     want = oracle.intersect(sc, origin, direc, max_ray_len, "port")
     g = GpuSeams(sc)
     try:
-        for R, chunks in ((0, 0), (4, 5), (1, 3)):
-            if R:
-                os.environ["LPCL_SEARCH_R"], os.environ["LPCL_SEARCH_CHUNKS"] = str(R), str(chunks)
+        for impl, R, chunks in (("simt", 0, 0), ("simt", 4, 5), ("simt", 1, 3), ("tc", 0, 0), ("tc", 1, 3), ("tc", 4, 5)):
+            _set_search(impl, R, chunks)
             try:
                 got = g.intersect(origin, direc, max_ray_len)
             finally:
-                os.environ.pop("LPCL_SEARCH_R", None), os.environ.pop("LPCL_SEARCH_CHUNKS", None)
-            assert np.array_equal(got[1], want[1]), "crossing counts differ (R=%d)" % R
-            assert np.array_equal(got[2], want[2]), "nearest triangle differs (R=%d)" % R
-            assert np.array_equal(util.bits(got[0]), util.bits(want[0])), "nearest t differs (R=%d)" % R
+                _clear_search()
+            assert np.array_equal(got[1], want[1]), "crossing counts differ (%s R=%d)" % (impl, R)
+            assert np.array_equal(got[2], want[2]), "nearest triangle differs (%s R=%d)" % (impl, R)
+            assert np.array_equal(util.bits(got[0]), util.bits(want[0])), "nearest t differs (%s R=%d)" % (impl, R)
     finally:
         g.close()
     assert (want[1] > 0).mean() > 0.3 and (want[1] > 1).sum() > 100  # the soup really is hit, often more than once
