@@ -53,14 +53,6 @@ __host__ __device__ inline int tc_canon(int row, int k, int rows) // float index
 {
     return (k >> 2) * rows * 4 + (row >> 3) * 32 + (row & 7) * 4 + (k & 3);
 }
-// dynamic shared memory of the kernel: padded past half an SM so that two CTAs (two 512-column
-// TMEM allocations) never share an SM
-__host__ __device__ constexpr int tc_smem_bytes(int rt)
-{
-    return (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + 256) > 120 * 1024 ? (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + 256)
-                                                                            : 120 * 1024;
-}
-
 // ------------------------------------------------------------------------------------------ scene build
 // one thread per (tile, triangle slot): three rows of 24 floats scattered into the canonical layout
 __global__ void build_tc_kernel(const float4 *v0, const float4 *v1, const float4 *v2, const TileInfo *tiles, int n_tiles,
@@ -144,43 +136,82 @@ __device__ __forceinline__ void tc_ld_48(uint32_t taddr, uint32_t *r)
 }
 
 // ------------------------------------------------------------------------------------------ exact path
-struct CandResult {
-    float t;   // nearest accepted t among the candidates (max_ray_len if none)
-    int tri;   // its triangle (-1 if none)
-    int hits;  // accepted candidates
-};
-// mask bit b = triangle tri_base + b passed the filter; evaluated in ascending triangle order with
-// a strict < so that the first index wins ties (cl:278)
-__device__ __noinline__ CandResult tc_candidates(unsigned mask, int tri_base, int tri_end, const float4 *tv0, const float4 *tv1,
-                                                 const float4 *tv2, const float4 *org_pow, const float4 *dir_prev,
-                                                 long long phys, float eps, float t_init)
+// Candidates are not evaluated where they are found: a lane that finds some appends (ray, triangle,
+// mesh) records to its warp's queue in shared memory and the sweep goes on.  When the queue is
+// half full (and at the end of the sweep) the whole warp drains it, one candidate per lane - the
+// exact evaluation runs with 32 active lanes instead of one or two, and its long memory latencies
+// no longer sit inside the MMA <-> epilogue hand-shake.  Accepted hits go straight to the scratch
+// with atomicAdd / atomicMin; the packed key (t bits, triangle) reproduces "first triangle index
+// wins ties" (cl:278) whatever the evaluation order.
+constexpr int TC_QUEUE_CAP = 256;   // records per warp
+constexpr int TC_QUEUE_DRAIN = 128; // drain threshold, checked once per accumulator
+
+__device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &rays, long long i, int tri, int mesh, float eps,
+                                             unsigned long long *key, int *cnt)
 {
-    CandResult res;
-    res.t = t_init;
-    res.tri = -1;
-    res.hits = 0;
-    const float4 o = org_pow[phys], d = dir_prev[phys];
-    while (mask) {
-        const int b = __ffs((int)mask) - 1;
-        mask &= mask - 1;
-        const int tri = tri_base + b;
-        if (tri >= tri_end) break;
-        const float4 a = __ldg(tv0 + tri), bb = __ldg(tv1 + tri), c = __ldg(tv2 + tri);
-        float t;
-        if (ray_triangle_exact(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z),
-                               v3(c.x, c.y, c.z), t) &&
-            t > eps) {
-            res.hits += 1;
-            if (t < res.t) {
-                res.t = t;
-                res.tri = tri;
-            }
+    const long long ph = rays.phys(i);
+    const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
+    const float4 a = __ldg(sc.v0 + tri), b = __ldg(sc.v1 + tri), c = __ldg(sc.v2 + tri);
+    float t;
+    if (ray_triangle_exact(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t) &&
+        t > eps) {
+        const long long slot = (long long)mesh * rays.n + i;
+        atomicAdd(&cnt[slot], 1);
+        atomicMin(&key[slot], pack_key(t, tri));
+    }
+}
+
+// warp-collective
+__device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev &sc, const RaysDev &rays, float eps,
+                                      unsigned long long *key, int *cnt)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int total = min(*q_count, TC_QUEUE_CAP);
+    for (int k = lane; k < total; k += 32) {
+        const int4 e = queue[k];
+        if (e.y >= 0) {
+            queue[k].y = -1; // holes left by an overflowing append stay negative
+            tc_exact_one(sc, rays, (long long)(unsigned)e.x, e.y, e.z, eps, key, cnt);
         }
     }
-    return res;
+    __syncwarp();
+    if (lane == 0) *q_count = 0;
+    __syncwarp();
+}
+
+// one lane, inside the divergent rare branch: mask bit b = triangle tri_base + b passed the filter
+__device__ __noinline__ void tc_enqueue(unsigned mask, int tri_base, long long i, int mesh, int4 *queue, int *q_count,
+                                        const SceneDev &sc, const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
+{
+    const int c = __popc(mask);
+    const int pos = atomicAdd(q_count, c);
+    if (pos + c <= TC_QUEUE_CAP) {
+        int k = pos;
+        while (mask) {
+            const int b = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            queue[k++] = make_int4((int)i, tri_base + b, mesh, 0);
+        }
+    } else { // queue full (pathological candidate density): evaluate in place
+        while (mask) {
+            const int b = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            tc_exact_one(sc, rays, i, tri_base + b, mesh, eps, key, cnt);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ the sweep
+constexpr int tc_queue_bytes() { return TC_EPI_WARPS * (TC_QUEUE_CAP * 16 + 16); }
+__host__ __device__ constexpr int tc_smem_bytes(int rt)
+{
+    // padded past half an SM so that two CTAs (two 512-column TMEM allocations) never share an SM
+    return (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + TC_EPI_WARPS * (TC_QUEUE_CAP * 16 + 16) + 256) > 120 * 1024
+               ? (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + TC_EPI_WARPS * (TC_QUEUE_CAP * 16 + 16) + 256)
+               : 120 * 1024;
+}
+
 template <int RT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *__restrict__ key, int *__restrict__ cnt,
@@ -189,7 +220,9 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *b_buf = reinterpret_cast<float *>(smem_raw);
     float *a_buf = reinterpret_cast<float *>(smem_raw + TC_STAGES * TC_TILE_BYTES);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + TC_STAGES * TC_TILE_BYTES + RT * TC_A_BYTES);
+    int4 *queues = reinterpret_cast<int4 *>(smem_raw + TC_STAGES * TC_TILE_BYTES + RT * TC_A_BYTES);
+    int *q_counts = reinterpret_cast<int *>(queues + TC_EPI_WARPS * TC_QUEUE_CAP); // one per 16 bytes
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(q_counts + TC_EPI_WARPS * 4);
     uint64_t *empty_bar = full_bar + TC_STAGES;
     uint64_t *tfull_bar = empty_bar + TC_STAGES; // [2] accumulator ready   (MMA commit -> epilogue)
     uint64_t *tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA issuer)
@@ -213,27 +246,23 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     }
     if (warp == TC_MMA_WARP) tc_alloc_512(tmem_slot);
 
-    // epilogue threads: per-ray state, and the A operand (each ray row written by one of its two threads)
+    // epilogue threads: the margin constant of each of their rays, the A operand (each ray row is
+    // written by one of its two threads) and an empty candidate queue
     const int row = (warp & 3) * 32 + lane; // TMEM lane == ray row of every ray tile
     const int half = (warp >> 2) & 1;
     const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
     const float eps = eps_len(max_ray_len);
-    float tmin[RT];
-    int best[RT], hits[RT];
     u64 k2[RT];
     if (warp < TC_EPI_WARPS) {
         const float vmax = *sc.vmax;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
-            // a row beyond the last ray sweeps a copy of the last ray (never flushed)
+            // a row beyond the last ray sweeps a copy of the last ray (its candidates are dropped)
             const long long i = min(ray0 + (long long)j * TC_M, rays.n - 1);
             const long long ph = rays.phys(i);
             const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
             const float kk = filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax);
             k2[j] = pack2(__float_as_uint(kk), __float_as_uint(kk));
-            tmin[j] = max_ray_len;
-            best[j] = -1;
-            hits[j] = 0;
             if ((j & 1) == half) {
                 const float a6[6] = {o.y * d.z - o.z * d.y, o.z * d.x - o.x * d.z, o.x * d.y - o.y * d.x, d.x, d.y, d.z};
                 float *dst = a_buf + j * TC_A_FLOATS;
@@ -248,6 +277,8 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 }
             }
         }
+        for (int k = lane; k < TC_QUEUE_CAP; k += 32) queues[warp * TC_QUEUE_CAP + k] = make_int4(0, -1, 0, 0);
+        if (lane == 0) q_counts[warp * 4] = 0;
     }
     fence_async_smem(); // generic-proxy writes of A -> visible to the tensor core's async proxy
     tc_fence_before();
@@ -291,55 +322,38 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
         }
     } else {
         unsigned n_cand = 0;
-        auto flush = [&](int mesh) {
-#pragma unroll
-            for (int j = 0; j < RT; ++j) {
-                const long long i = ray0 + (long long)j * TC_M;
-                if (i < rays.n) {
-                    const long long slot = (long long)mesh * rays.n + i;
-                    if (hits[j]) atomicAdd(&cnt[slot], hits[j]);
-                    if (best[j] >= 0) atomicMin(&key[slot], pack_key(tmin[j], best[j]));
-                }
-                tmin[j] = max_ray_len;
-                best[j] = -1;
-                hits[j] = 0;
-            }
-        };
+        int4 *queue = queues + warp * TC_QUEUE_CAP;
+        int *q_count = q_counts + warp * 4;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        int cur_mesh = -1;
         for (int it = 0; it < nt; ++it) {
             const int4 ti4 = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it));
             const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
-            if (mesh != cur_mesh) {
-                if (cur_mesh >= 0) flush(cur_mesh);
-                cur_mesh = mesh;
-            }
+            // this warp's share of the tile: chunks 2 half and 2 half + 1 (16 triangles = 48 columns each)
+            const int n_chunks = min(max((count - half * 2 * TC_CHUNK_TRIS + TC_CHUNK_TRIS - 1) / TC_CHUNK_TRIS, 0), 2);
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
                 const int g = it * RT + j, buf = g & 1;
                 mbar_wait(&tfull_bar[buf], (unsigned)((g >> 1) & 1));
                 tc_fence_after();
+                uint32_t r[2][48];
+                const uint32_t col = (uint32_t)(buf * TC_ACC_STRIDE + half * 2 * 48);
+                if (n_chunks > 0) tc_ld_48(lane_addr + col, r[0]);
+                if (n_chunks > 1) tc_ld_48(lane_addr + col + 48u, r[1]);
+                tc_wait_ld();
+                tc_fence_before(); // the accumulator is in registers: hand it back before computing
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 const long long i = ray0 + (long long)j * TC_M;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    const int chunk = half * 2 + cc; // 16 triangles, 48 columns
-                    if (chunk * TC_CHUNK_TRIS < count) {
-                        uint32_t r[48];
-                        __syncwarp(); // reconverge after a divergent exact path: tcgen05.ld is warp-collective
-                        tc_ld_48(lane_addr + (uint32_t)(buf * TC_ACC_STRIDE + chunk * 48), r);
-                        tc_wait_ld();
-                        if (cc == 1 || (chunk + 1) * TC_CHUNK_TRIS >= count) { // last read of this accumulator by this warp
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-                        }
+                    if (cc < n_chunks) {
                         u64 pu[8], pv[8];
                         unsigned none = 0xffffffffu; // sign bit survives only if every test of the chunk failed
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const u64 den = pack2(r[6 * q + 0], r[6 * q + 1]);
-                            const u64 un = pack2(r[6 * q + 2], r[6 * q + 3]);
-                            const u64 vn = pack2(r[6 * q + 4], r[6 * q + 5]);
+                            const u64 den = pack2(r[cc][6 * q + 0], r[cc][6 * q + 1]);
+                            const u64 un = pack2(r[cc][6 * q + 2], r[cc][6 * q + 3]);
+                            const u64 vn = pack2(r[cc][6 * q + 4], r[cc][6 * q + 5]);
                             pu[q] = ffma2(un, fsub2(den, un), k2[j]); // uN' (DEN' - uN') + K2
                             pv[q] = ffma2(vn, fsub2(den, vn), k2[j]); // vN' (DEN' - vN') + K2
                             none = or_and(lo32(pu[q]), lo32(pv[q]), none);
@@ -352,27 +366,19 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                                 mask |= ((~(lo32(pu[q]) | lo32(pv[q]))) >> 31) << (2 * q);
                                 mask |= ((~(hi32(pu[q]) | hi32(pv[q]))) >> 31) << (2 * q + 1);
                             }
+                            const int first = (half * 2 + cc) * TC_CHUNK_TRIS;
+                            if (count - first < TC_CHUNK_TRIS) mask &= (1u << (count - first)) - 1u; // padding
                             n_cand += __popc(mask);
-                            if (i < rays.n) {
-                                const CandResult cr =
-                                    tc_candidates(mask, tri0 + chunk * TC_CHUNK_TRIS, tri0 + count, sc.v0, sc.v1, sc.v2,
-                                                  rays.org_pow, rays.dir_prev, rays.phys(i), eps, max_ray_len);
-                                hits[j] += cr.hits;
-                                if (cr.tri >= 0 && cr.t < tmin[j]) { // strict: earlier chunks hold lower triangle indices
-                                    tmin[j] = cr.t;
-                                    best[j] = cr.tri;
-                                }
-                            }
+                            if (mask && i < rays.n)
+                                tc_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
                         }
-                    } else if (cc == 0) { // nothing to read in this accumulator for this warp: release it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                     }
                 }
+                __syncwarp();
+                if (*(volatile int *)q_count >= TC_QUEUE_DRAIN) tc_drain(queue, q_count, sc, rays, eps, key, cnt);
             }
         }
-        if (cur_mesh >= 0) flush(cur_mesh);
+        tc_drain(queue, q_count, sc, rays, eps, key, cnt);
         if (cand_total) {
             for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
             if (lane == 0 && n_cand) atomicAdd(cand_total, (unsigned long long)n_cand);
