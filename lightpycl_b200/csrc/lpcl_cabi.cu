@@ -295,15 +295,16 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         if (blocks > (long long)s->sm_count * 32) blocks = (long long)s->sm_count * 32;
         scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key);
     }
-    // LPCL_SEARCH_IMPL=tc: filter on the tensor cores (lpcl_search_tc.cuh); simt: packed-FP32 filter
+    // Default: the filter on the tensor cores (lpcl_search_tc.cuh).  LPCL_SEARCH_IMPL=simt selects the
+    // packed-FP32 filter (lpcl_search.cuh) - kept as the second implementation the tests cross-check.
     const char *impl = getenv("LPCL_SEARCH_IMPL");
-    if (impl && !strcmp(impl, "tc")) {
+    if (!impl || strcmp(impl, "simt") != 0) {
         const int want_rt = env_int("LPCL_SEARCH_RT", 0);
         int v = -1;
         for (int k = 0; k < kNumTcVariants; ++k)
             if (kTcVariants[k].rt == want_rt) v = k;
-        if (v < 0) {
-            v = kNumTcVariants - 1;
+        if (v < 0) { // 4 ray tiles per CTA (measured best on C3), fewer while the ray blocks would be mostly padding
+            v = 2;
             while (v > 0 && n < 8LL * kTcVariants[v].rt * TC_M) --v;
         }
         const int64_t per_cta = (int64_t)kTcVariants[v].rt * TC_M;

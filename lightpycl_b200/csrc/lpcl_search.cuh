@@ -95,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "{\n"
         ".reg .pred p;\n"
         "LPCL_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n" // suspend-time hint: sleep, do not spin
         "@p bra LPCL_DONE;\n"
         "bra LPCL_WAIT;\n"
         "LPCL_DONE:\n"

@@ -17,10 +17,15 @@
 // candidates to the exact, reference-ordered evaluation, which alone decides results.
 //
 // CTA = 10 warps, one CTA per SM:
-//   warps 0-7  epilogue; warp w reads TMEM lanes 32 (w % 4) .. +31 (its rays) and the triangle
-//              chunks of half w / 4; they also stage the A operand (RT ray tiles) once per CTA;
+//   warps 0-7  epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its rays) and the two
+//              16-triangle chunks of half w / 4 of EVERY (ray tile, triangle tile) step, software
+//              pipelined over two 48-register buffers (the tcgen05.ld of the next chunk is in flight
+//              while this one is tested).  Few fat warps keep the per-step overhead (barrier wait,
+//              fences, release) per SM sub-partition small - the sub-partition's issue slots, not
+//              the tensor pipe, are the scarce resource (profiles/r1_tc_notes.txt).  The epilogue
+//              warps also stage the A operand (RT ray tiles) once per CTA;
 //   warp 8     TMA producer: one bulk copy (18 KB) per triangle tile, TC_STAGES deep;
-//   warp 9     MMA issuer (one lane): waits tile + free accumulator, issues 3 MMAs, commits.
+//   warp 9     MMA issuer (one elected lane): waits tile + free accumulator, issues 3 MMAs, commits.
 // Shared-memory operands use the no-swizzle K-major canonical layout (8-row x 16-byte core
 // matrices): element (row, k) at (k / 4) * rows * 16 + (row / 8) * 128 + (row % 8) * 16 + (k % 4) * 4.
 // The triangle tiles are stored in exactly that layout in global memory, so a tile is one 1-D TMA
@@ -101,6 +106,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool tc_elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // shared-memory matrix descriptor: no swizzle, K-major; LBO = bytes between the two 16-byte K halves
 // of one MMA, SBO = bytes between 8-row groups
 __device__ __forceinline__ uint64_t tc_smem_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes)
@@ -180,9 +192,20 @@ __device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev 
     __syncwarp();
 }
 
+// queue full (pathological candidate density): evaluate in place
+__device__ __noinline__ void tc_overflow(unsigned mask, int tri_base, long long i, int mesh, const SceneDev &sc,
+                                         const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
+{
+    while (mask) {
+        const int b = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        tc_exact_one(sc, rays, i, tri_base + b, mesh, eps, key, cnt);
+    }
+}
+
 // one lane, inside the divergent rare branch: mask bit b = triangle tri_base + b passed the filter
-__device__ __noinline__ void tc_enqueue(unsigned mask, int tri_base, long long i, int mesh, int4 *queue, int *q_count,
-                                        const SceneDev &sc, const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
+__device__ __forceinline__ void tc_enqueue(unsigned mask, int tri_base, long long i, int mesh, int4 *queue, int *q_count,
+                                           const SceneDev &sc, const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
 {
     const int c = __popc(mask);
     const int pos = atomicAdd(q_count, c);
@@ -193,12 +216,8 @@ __device__ __noinline__ void tc_enqueue(unsigned mask, int tri_base, long long i
             mask &= mask - 1;
             queue[k++] = make_int4((int)i, tri_base + b, mesh, 0);
         }
-    } else { // queue full (pathological candidate density): evaluate in place
-        while (mask) {
-            const int b = __ffs((int)mask) - 1;
-            mask &= mask - 1;
-            tc_exact_one(sc, rays, i, tri_base + b, mesh, eps, key, cnt);
-        }
+    } else {
+        tc_overflow(mask, tri_base, i, mesh, sc, rays, eps, key, cnt);
     }
 }
 
@@ -286,96 +305,116 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The producer and MMA warps run their loops warp-converged and elect the issuing lane with
+    // elect.sync: addresses and descriptors then live in uniform registers and each tcgen05.mma is
+    // a single UTCHMMA (a plain `if (lane == 0)` makes nvcc wrap every one in an election loop fed
+    // by R2UR moves - measured 330 + 300 cycles of issue-thread time per step instead of ~100).
     if (warp == TC_PRODUCER_WARP) {
-        if (lane == 0) {
-            for (int it = 0; it < nt; ++it) {
-                const int s = it % TC_STAGES;
-                if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (unsigned)((it / TC_STAGES - 1) & 1));
+        for (int it = 0; it < nt; ++it) {
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (unsigned)((it / TC_STAGES - 1) & 1));
+            if (tc_elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[s], TC_TILE_BYTES);
                 tma_load_bulk(b_buf + s * TC_TILE_FLOATS, sc.tc_filter + (long long)(c0 + it) * TC_TILE_FLOATS, TC_TILE_BYTES,
                               &full_bar[s]);
             }
+            __syncwarp();
         }
     } else if (warp == TC_MMA_WARP) {
-        if (lane == 0) {
-            const unsigned a_addr = smem_u32(a_buf), b_addr = smem_u32(b_buf);
-            for (int it = 0; it < nt; ++it) {
-                const int s = it % TC_STAGES;
-                mbar_wait(&full_bar[s], (unsigned)((it / TC_STAGES) & 1));
-                tc_fence_after();
-#pragma unroll 1
-                for (int j = 0; j < RT; ++j) {
-                    const int g = it * RT + j, buf = g & 1, use = g >> 1;
-                    if (use > 0) mbar_wait(&tempty_bar[buf], (unsigned)((use - 1) & 1));
-                    tc_fence_after();
-                    const uint32_t acc = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
+        // descriptors differ only in their start-address field (bits 0-13, 16-byte units)
+        const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_buf), TC_M * 16, 128);
+        const uint64_t b_desc0 = tc_smem_desc(smem_u32(b_buf), TC_N * 16, 128);
+        int g = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(&full_bar[s], (unsigned)((it / TC_STAGES) & 1));
+            tc_fence_after();
+            const uint64_t db = b_desc0 + (uint64_t)((s * TC_TILE_BYTES) >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const uint64_t da = tc_smem_desc(a_addr + j * TC_A_BYTES + ks * 2 * TC_M * 16, TC_M * 16, 128);
-                        const uint64_t db = tc_smem_desc(b_addr + s * TC_TILE_BYTES + ks * 2 * TC_N * 16, TC_N * 16, 128);
-                        tc_mma_tf32(acc, da, db, ks > 0 ? 1u : 0u);
-                    }
+            for (int j = 0; j < RT; ++j, ++g) {
+                const int buf = g & 1, use = g >> 1;
+                if (use > 0) mbar_wait(&tempty_bar[buf], (unsigned)((use - 1) & 1));
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
+                const uint64_t da = a_desc0 + (uint64_t)((j * TC_A_BYTES) >> 4);
+                if (tc_elect_one()) {
+                    tc_mma_tf32(acc, da, db, 0u);
+                    tc_mma_tf32(acc, da + (uint64_t)((2 * TC_M * 16) >> 4), db + (uint64_t)((2 * TC_N * 16) >> 4), 1u);
+                    tc_mma_tf32(acc, da + (uint64_t)((4 * TC_M * 16) >> 4), db + (uint64_t)((4 * TC_N * 16) >> 4), 1u);
                     tc_commit(&tfull_bar[buf]);
+                    if (j == RT - 1) tc_commit(&empty_bar[s]); // the tile's shared-memory slot is free once its MMAs completed
                 }
-                tc_commit(&empty_bar[s]); // the tile's shared-memory slot is free once its MMAs have completed
+                __syncwarp();
             }
         }
     } else {
         unsigned n_cand = 0;
         int4 *queue = queues + warp * TC_QUEUE_CAP;
         int *q_count = q_counts + warp * 4;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int chunk0 = half * 2; // this warp tests chunks chunk0 and chunk0 + 1 (16 triangles = 48 columns each)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk0 * 48);
+        const int steps = nt * RT;
+        uint32_t rA[48], rB[48];
+
+        // the two product tests on 16 triangles x this lane's ray; candidates go to the warp's queue
+        auto test_chunk = [&](const uint32_t(&r)[48], u64 kk, int first, int tri0, int count, int mesh, long long i) {
+            u64 du[8], dv[8];
+            unsigned none[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}; // a sign bit survives only if every test failed
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const u64 den = pack2(r[6 * q + 0], r[6 * q + 1]);
+                const u64 un = pack2(r[6 * q + 2], r[6 * q + 3]);
+                const u64 vn = pack2(r[6 * q + 4], r[6 * q + 5]);
+                du[q] = ffma2(un, fsub2(den, un), kk); // uN' (DEN' - uN') + K2
+                dv[q] = ffma2(vn, fsub2(den, vn), kk); // vN' (DEN' - vN') + K2
+                none[(2 * q) & 3] = or_and(lo32(du[q]), lo32(dv[q]), none[(2 * q) & 3]);
+                none[(2 * q + 1) & 3] = or_and(hi32(du[q]), hi32(dv[q]), none[(2 * q + 1) & 3]);
+            }
+            if ((int)(none[0] & none[1] & none[2] & none[3]) >= 0) { // rare: a triangle of the chunk passed both tests
+                unsigned mask = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    mask |= ((~(lo32(du[q]) | lo32(dv[q]))) >> 31) << (2 * q);
+                    mask |= ((~(hi32(du[q]) | hi32(dv[q]))) >> 31) << (2 * q + 1);
+                }
+                const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
+                if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
+                n_cand += __popc(mask);
+                if (mask && i < rays.n) tc_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
+            }
+            __syncwarp(); // reconverge: tcgen05.ld and the barrier hand-shake are warp-collective
+        };
+
+        if (steps > 0) { // prologue: step 0 into both buffers
+            mbar_wait(&tfull_bar[0], 0u);
+            tc_fence_after();
+            tc_ld_48(lane_addr, rA);
+            tc_ld_48(lane_addr + 48u, rB);
+        }
+        int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
         for (int it = 0; it < nt; ++it) {
-            const int4 ti4 = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it));
+            const int4 ti4 = ti_next; // fetched one tile ahead: the L2 latency is off the critical path
+            if (it + 1 < nt) ti_next = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it + 1));
             const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
-            // this warp's share of the tile: chunks 2 half and 2 half + 1 (16 triangles = 48 columns each)
-            const int n_chunks = min(max((count - half * 2 * TC_CHUNK_TRIS + TC_CHUNK_TRIS - 1) / TC_CHUNK_TRIS, 0), 2);
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
                 const int g = it * RT + j, buf = g & 1;
-                mbar_wait(&tfull_bar[buf], (unsigned)((g >> 1) & 1));
-                tc_fence_after();
-                uint32_t r[2][48];
-                const uint32_t col = (uint32_t)(buf * TC_ACC_STRIDE + half * 2 * 48);
-                if (n_chunks > 0) tc_ld_48(lane_addr + col, r[0]);
-                if (n_chunks > 1) tc_ld_48(lane_addr + col + 48u, r[1]);
-                tc_wait_ld();
-                tc_fence_before(); // the accumulator is in registers: hand it back before computing
+                const bool more = g + 1 < steps;
+                const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
+                const long long i = ray0 + (long long)j * TC_M;
+                tc_wait_ld(); // both chunks of step g are in registers: hand the accumulator back
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-                const long long i = ray0 + (long long)j * TC_M;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    if (cc < n_chunks) {
-                        u64 pu[8], pv[8];
-                        unsigned none = 0xffffffffu; // sign bit survives only if every test of the chunk failed
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const u64 den = pack2(r[cc][6 * q + 0], r[cc][6 * q + 1]);
-                            const u64 un = pack2(r[cc][6 * q + 2], r[cc][6 * q + 3]);
-                            const u64 vn = pack2(r[cc][6 * q + 4], r[cc][6 * q + 5]);
-                            pu[q] = ffma2(un, fsub2(den, un), k2[j]); // uN' (DEN' - uN') + K2
-                            pv[q] = ffma2(vn, fsub2(den, vn), k2[j]); // vN' (DEN' - vN') + K2
-                            none = or_and(lo32(pu[q]), lo32(pv[q]), none);
-                            none = or_and(hi32(pu[q]), hi32(pv[q]), none);
-                        }
-                        if ((int)none >= 0) { // rare: some triangle of the chunk passed both tests for this ray
-                            unsigned mask = 0;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                mask |= ((~(lo32(pu[q]) | lo32(pv[q]))) >> 31) << (2 * q);
-                                mask |= ((~(hi32(pu[q]) | hi32(pv[q]))) >> 31) << (2 * q + 1);
-                            }
-                            const int first = (half * 2 + cc) * TC_CHUNK_TRIS;
-                            if (count - first < TC_CHUNK_TRIS) mask &= (1u << (count - first)) - 1u; // padding
-                            n_cand += __popc(mask);
-                            if (mask && i < rays.n)
-                                tc_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
-                        }
-                    }
-                }
-                __syncwarp();
                 if (*(volatile int *)q_count >= TC_QUEUE_DRAIN) tc_drain(queue, q_count, sc, rays, eps, key, cnt);
+                test_chunk(rA, k2[j], chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                if (more) { // the first chunk of step g + 1 loads while the second chunk of step g is tested
+                    mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
+                    tc_fence_after();
+                    tc_ld_48(next_addr, rA);
+                }
+                test_chunk(rB, k2[j], (chunk0 + 1) * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                if (more) tc_ld_48(next_addr + 48u, rB);
             }
         }
         tc_drain(queue, q_count, sc, rays, eps, key, cnt);

@@ -126,6 +126,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
+// A operand read from TMEM (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -208,8 +216,9 @@ __global__ void mma_check_kernel(const float *a, const float *b, const float *c_
     if (warp == 0) tmem_free_512(base);
 }
 
-__global__ void mma_rate_kernel(unsigned long long *cycles, int n_mma, int ksteps)
+__global__ void mma_rate_kernel(unsigned long long *cycles, int n_mma, int ksteps, int nn, int ts)
 {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t base_slot;
     __shared__ __align__(8) uint64_t bar;
@@ -228,11 +237,26 @@ __global__ void mma_rate_kernel(unsigned long long *cycles, int n_mma, int kstep
     long long t0 = 0, t1 = 0;
     if (threadIdx.x == 0) {
         t0 = clock64();
-        for (int i = 0; i < n_mma; ++i) {
-            const int s = i % ksteps;
-            const uint64_t da = smem_desc(smem_u32(sa) + s * 2 * MM * 16, MM * 16, 128);
-            const uint64_t db = smem_desc(smem_u32(sb) + s * 2 * NN * 16, NN * 16, 128);
-            mma_tf32(base + (uint32_t)((i / ksteps) & 1) * 256u, da, db, IDESC, s > 0 ? 1u : 0u);
+        // descriptors precomputed and the 3 k-steps unrolled: the loop measures the tensor core, not this thread
+        uint64_t da[3], db[3];
+        for (int s = 0; s < 3; ++s) {
+            da[s] = smem_desc(smem_u32(sa) + s * 2 * MM * 16, MM * 16, 128);
+            db[s] = smem_desc(smem_u32(sb) + s * 2 * nn * 16, nn * 16, 128);
+        }
+        if (ts) {
+            for (int i = 0; i < n_mma / 3; ++i) {
+                const uint32_t d = base + (uint32_t)(i & 1) * 256u;
+                mma_tf32_ts(d, base + 448u, db[0], idesc, 0u);
+                mma_tf32_ts(d, base + 456u, db[1], idesc, 1u);
+                mma_tf32_ts(d, base + 464u, db[2], idesc, 1u);
+            }
+        } else {
+            for (int i = 0; i < n_mma / 3; ++i) {
+                const uint32_t d = base + (uint32_t)(i & 1) * 256u;
+                mma_tf32(d, da[0], db[0], idesc, 0u);
+                mma_tf32(d, da[1], db[1], idesc, 1u);
+                mma_tf32(d, da[2], db[2], idesc, 1u);
+            }
         }
         mma_commit(&bar);
         mbar_wait(&bar, 0);
@@ -336,14 +360,107 @@ static void run_mma()
         std::vector<unsigned long long> h(sms);
         const int ks = 3, smem = (MM + NN) * 8 * ks * 4;
         CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        for (int n_mma = 300; n_mma <= 3000; n_mma *= 10) {
-            for (int rep = 0; rep < 2; ++rep) { mma_rate_kernel<<<sms, 128, smem>>>(cyc, n_mma, ks); CK(cudaDeviceSynchronize()); }
+        const int n_mma = 3000;
+        for (int ts = 0; ts < 2; ++ts)
+        for (int nn = 64; nn <= (ts ? 192 : 256); nn += 32) {
+            for (int rep = 0; rep < 2; ++rep) { mma_rate_kernel<<<sms, 128, smem>>>(cyc, n_mma, ks, nn, ts); CK(cudaDeviceSynchronize()); }
             CK(cudaMemcpy(h.data(), cyc, sms * 8, cudaMemcpyDeviceToHost));
             double mean = 0; for (int i = 0; i < sms; ++i) mean += (double)h[i]; mean /= sms;
-            printf("mma tf32 128x256x8: %d back-to-back on %d SMs: %.1f cycles each  (%.0f flop/clk/SM)\n", n_mma, sms, mean / n_mma,
-                   2.0 * MM * NN * 8 * n_mma / mean);
+            printf("mma tf32 %s 128x%dx8: %d back-to-back on %d SMs: %.1f cycles each  (%.0f flop/clk/SM)\n", ts ? "A in TMEM" : "A in smem", nn, n_mma, sms, mean / n_mma,
+                   2.0 * MM * nn * 8 * n_mma / mean);
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// (C) do tcgen05.ld and tcgen05.mma share a TMEM port?  `ld_warps` warps stream x32 loads from
+// columns 384.. while (optionally) one more warp issues 128x192x8 MMAs into columns 0..383.
+__global__ void contention_kernel(unsigned long long *cycles, unsigned *sink, int iters, int n_mma, int ld_warps, int do_mma)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t base_slot;
+    __shared__ __align__(8) uint64_t bar;
+    float *sa = (float *)smem, *sb = sa + MM * 24;
+    const int warp = threadIdx.x >> 5;
+    const int nn = 192;
+    for (int i = threadIdx.x; i < (MM + nn) * 24; i += blockDim.x) sa[i] = 1.0f;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    if (warp == 0) tmem_alloc_512(&base_slot);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = base_slot;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
+    uint32_t acc = 0;
+    if (warp < ld_warps) {
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            uint32_t r[32];
+            tmem_ld_x32(base + lane_field + 384u + (uint32_t)(((i + (warp >> 2)) * 32) & 127), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) acc ^= r[k] ^ r[k + 1];
+        }
+        const long long t1 = clock64();
+        if ((threadIdx.x & 31) == 0) cycles[blockIdx.x * 32 + warp] = (unsigned long long)(t1 - t0);
+    } else if (warp == ld_warps && do_mma) {
+        if ((threadIdx.x & 31) == 0) {
+            uint64_t da[3], db[3];
+            for (int s = 0; s < 3; ++s) {
+                da[s] = smem_desc(smem_u32(sa) + s * 2 * MM * 16, MM * 16, 128);
+                db[s] = smem_desc(smem_u32(sb) + s * 2 * nn * 16, nn * 16, 128);
+            }
+            const long long t0 = clock64();
+            for (int i = 0; i < n_mma / 3; ++i) {
+                const uint32_t d = base + (uint32_t)(i & 1) * 192u;
+                mma_tf32(d, da[0], db[0], idesc, 0u);
+                mma_tf32(d, da[1], db[1], idesc, 1u);
+                mma_tf32(d, da[2], db[2], idesc, 1u);
+            }
+            mma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t1 = clock64();
+            cycles[blockIdx.x * 32 + 31] = (unsigned long long)(t1 - t0);
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free_512(base);
+}
+
+static void run_contention()
+{
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    unsigned long long *cyc;
+    unsigned *sink;
+    CK(cudaMalloc(&cyc, sms * 32 * 8));
+    CK(cudaMalloc(&sink, 4));
+    std::vector<unsigned long long> h(sms * 32);
+    const int smem = (MM + 192) * 24 * 4;
+    CK(cudaFuncSetAttribute(contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int ld_warps = 4; ld_warps <= 16; ld_warps *= 2)
+        for (int do_mma = 0; do_mma < 2; ++do_mma) {
+            const int iters = 3000, n_mma = 9000; // ~290 k cycles of MMAs, ~290 k cycles of loads
+            CK(cudaMemset(cyc, 0, sms * 32 * 8));
+            for (int rep = 0; rep < 2; ++rep) {
+                contention_kernel<<<sms, (ld_warps + 1) * 32, smem>>>(cyc, sink, iters, n_mma, ld_warps, do_mma);
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(h.data(), cyc, sms * 32 * 8, cudaMemcpyDeviceToHost));
+            double ld = 0, mma = 0;
+            for (int b = 0; b < sms; ++b) { for (int w = 0; w < ld_warps; ++w) ld += (double)h[b * 32 + w]; mma += (double)h[b * 32 + 31]; }
+            ld /= (double)sms * ld_warps; mma /= sms;
+            printf("contention: %2d ld warps, mma %d : %.1f cycles per x32 load per warp (%.0f B/clk/SM)", ld_warps, do_mma, ld / iters,
+                   (double)iters * ld_warps * 4096.0 / ld);
+            if (do_mma) printf("   %.1f cycles per 128x192x8 MMA", mma / n_mma);
+            printf("\n");
+        }
 }
 
 int main(int argc, char **argv)
@@ -352,6 +469,7 @@ int main(int argc, char **argv)
     CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, %d MHz\n", p.name, p.multiProcessorCount, p.clockRate / 1000);
     if (argc > 1 && !strcmp(argv[1], "mma")) run_mma();
+    else if (argc > 1 && !strcmp(argv[1], "contention")) run_contention();
     else run_ldtm();
     return 0;
 }
