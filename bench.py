@@ -319,16 +319,55 @@ def main_native(args):
     fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # TFLOP/s: SMs x 128 lanes x 2 x f_SM
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dram bytes per launch from the committed `ncu --set full` capture of this same workload
-    traffic = {"search_kernel": None, "step_kernel": None}
-    try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        for k in traffic:
-            v = cap["kernels"].get(k, [{}])[0]
-            tot = v.get("dram_read_bytes", float("nan")) + v.get("dram_write_bytes", float("nan"))
-            traffic[k] = tot if tot == tot else None  # NaN -> null
-    except Exception:
-        pass
+    traffic = {"search_kernel": None, "search_tc_kernel": None, "step_kernel": None}
+    for cap_file in ("r1_ncu_traffic.json", "r1tc_ncu_traffic.json"):  # packed-FP32 search capture, tensor-core search capture
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", cap_file)))
+            for k in traffic:
+                if k in cap["kernels"] and (traffic[k] is None or cap_file.startswith("r1tc")):
+                    v = cap["kernels"][k][0]
+                    tot = v.get("dram_read_bytes", float("nan")) + v.get("dram_write_bytes", float("nan"))
+                    traffic[k] = tot if tot == tot else traffic[k]  # NaN -> keep
+        except Exception:
+            pass
     search_tflops = FLOP_PER_TEST * (rays_total * tri) / (search_ms * 1e-3) / 1e12 if search_ms else 0.0
+    tests_per_s_kernel = (rays_total * tri) / (search_ms * 1e-3) if search_ms else 0.0
+    simt = os.environ.get("LPCL_SEARCH_IMPL", "tc") == "simt"
+    if simt:
+        roofline = {
+            "kernel": "lpcl::search_kernel", "bound": "fp32", "achieved": search_tflops, "peak": fp32_peak,
+            "unit": "TFLOP/s", "frac": search_tflops / fp32_peak if fp32_peak else None,
+            "traffic": traffic["search_kernel"], "traffic_note": "dram read+write bytes per launch, ncu --set full "
+            "(profiles/r1_ncu_traffic.json); algorithmic DRAM bytes per launch = 32 B/ray + 64 B/triangle",
+            "peak_source": "SMs x 128 FP32 lanes x 2 x sm_max_mhz (%d x 128 x 2 x %.0f MHz); the packed-FP32 search is "
+                           "FMA-pipe bound; MEASURED_PEAKS.json has no FP32 entry" % (sm_count, sm_max_mhz),
+            "algorithmic_flop_per_test": FLOP_PER_TEST,
+            "note": "LPCL_SEARCH_IMPL=simt: frac uses the reference formulation's 52 FLOP/test (SURVEY.md 8(d)); the kernel "
+                    "executes 19.25 FMA-pipe lane-ops (packed FFMA2) + 1 ALU op per test, so frac can exceed 1; ncu "
+                    "sm__pipe_fma_cycles_active = 77% (profiles/r1_search_kernel_0_ncu.txt)",
+        }
+    else:
+        # the default search evaluates the filter as a split-TF32 GEMM: 3 outputs x K = 24 multiply-adds per test
+        tc_flop = 3 * 24 * 2.0
+        tf32_peak = float(peaks.get("bf16_tflops", 1681.8)) / 2.0
+        tc_tflops = tc_flop * tests_per_s_kernel / 1e12
+        roofline = {
+            "kernel": "lpcl::search_tc_kernel", "bound": "tensor", "achieved": tc_tflops, "peak": tf32_peak,
+            "unit": "TFLOP/s", "frac": tc_tflops / tf32_peak if tf32_peak else None,
+            "traffic": traffic["search_tc_kernel"], "traffic_note": "dram read+write bytes per launch, ncu --set full "
+            "(profiles/r1tc_ncu_traffic.json); algorithmic DRAM bytes per launch = 32 B/ray + 288 B/triangle + results",
+            "peak_source": "kind::tf32 tcgen05.mma runs at half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2 "
+                           "(tools/ubench_tmem.cu measures 4092 tf32 flop/clk/SM = 1190 TFLOP/s at 1965 MHz unthrottled)",
+            "algorithmic_flop_per_test": tc_flop,
+            "note": "flops are the tensor-core work of this formulation (DESIGN.md: DEN/uN/vN as a K=24 split-TF32 GEMM), not "
+                    "the reference's 52 fp32 FLOP/test; with the latter the kernel runs at %.1f TFLOP/s = %.2f of the "
+                    "%.1f TFLOP/s fp32 lane peak.  The tensor pipe is ~30%% busy: the kernel is bound by the CUDA-core "
+                    "epilogue that reads the accumulator back (tcgen05.ld) and applies the product tests "
+                    "(profiles/r1_tc_notes.txt)" % (search_tflops, search_tflops / fp32_peak, fp32_peak),
+        }
+    roofline.update({"launches": n_search, "avg_launch_ms": search_ms / max(n_search, 1),
+                     "tests_per_s_kernel": tests_per_s_kernel,
+                     "share_of_step": search_ms / sum(step_ms) if step_ms else None})
     resolve_gbs = resolve_bytes / (resolve_ms * 1e-3) / 1e9 if resolve_ms else 0.0
 
     line = {
@@ -343,22 +382,7 @@ def main_native(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {
-            "kernel": "lpcl::search_kernel", "bound": "fp32", "achieved": search_tflops, "peak": fp32_peak,
-            "unit": "TFLOP/s", "frac": search_tflops / fp32_peak if fp32_peak else None,
-            "traffic": traffic["search_kernel"], "traffic_note": "dram read+write bytes per launch, ncu --set full "
-            "(profiles/r1_ncu_traffic.json); algorithmic DRAM bytes per launch = 32 B/ray + 64 B/triangle",
-            "peak_source": "SMs x 128 FP32 lanes x 2 x sm_max_mhz (%d x 128 x 2 x %.0f MHz); the search is "
-                           "FMA-pipe bound, neither HBM nor tensor (SURVEY.md 8(d)); MEASURED_PEAKS.json has no "
-                           "FP32 entry" % (sm_count, sm_max_mhz),
-            "algorithmic_flop_per_test": FLOP_PER_TEST, "launches": n_search,
-            "note": "frac uses the reference formulation's 52 FLOP/test (SURVEY.md 8(d)); the kernel executes "
-                    "19.25 FMA-pipe lane-ops (packed FFMA2) + 1 ALU op per test, so frac can exceed 1; ncu "
-                    "sm__pipe_fma_cycles_active = 77% (profiles/r1_search_kernel_0_ncu.txt)",
-            "avg_launch_ms": search_ms / max(n_search, 1),
-            "tests_per_s_kernel": (rays_total * tri) / (search_ms * 1e-3) if search_ms else 0.0,
-            "share_of_step": search_ms / sum(step_ms) if step_ms else None,
-        },
+        "roofline": roofline,
         "roofline_material": {
             "kernel": "lpcl::step_kernel", "bound": "hbm", "achieved": resolve_gbs, "peak": hbm_peak, "unit": "GB/s",
             "frac": resolve_gbs / hbm_peak if hbm_peak else None, "traffic": traffic["step_kernel"],

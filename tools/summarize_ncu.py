@@ -32,6 +32,9 @@ KEYS = [
     "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "smsp__average_warp_latency_per_inst_issued.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "smsp__sass_inst_executed_op_tmem_ldt.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active",
 ]
 PREFIXES = ["smsp__average_warps_issue_stalled_"]
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
