@@ -406,7 +406,8 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-                if (*(volatile int *)q_count >= TC_QUEUE_DRAIN) tc_drain(queue, q_count, sc, rays, eps, key, cnt);
+                if (j == 0 && *(volatile int *)q_count >= TC_QUEUE_DRAIN) // once per triangle tile; an overflowing append evaluates in place
+                    tc_drain(queue, q_count, sc, rays, eps, key, cnt);
                 test_chunk(rA, k2[j], chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
                 if (more) { // the first chunk of step g + 1 loads while the second chunk of step g is tested
                     mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
