@@ -15,8 +15,10 @@ triangles, depth 10" (parabolic mirror + terminator + measure dome, 100,552 tria
           light_source, meshes, ...) + get_measured_rays() - with HOST NumPy inputs: host
           flattening, host->device copies of rays and geometry, scene build and the device->host
           read of the measured (pos, pwr) are all inside the timed region.
-  roofline            the dominant kernel (nearest-hit search): algorithmic 52 FLOP per test
-                       over its CUDA-event time, against the FP32 FMA peak.
+  roofline            the dominant kernel (nearest-hit search) over its CUDA-event time: the default
+                      tensor-core search does 144 tf32 flop per test (3 outputs x K = 24), bound
+                      "tensor", peak = MEASURED_PEAKS bf16_tflops / 2; with LPCL_SEARCH_IMPL=simt the
+                      packed-FP32 search, 52 FLOP per test against the FP32 lane peak.
   roofline_material   the fused resolve/Fresnel/compaction kernel against measured HBM bandwidth.
   cpu_baseline        the reference kernels (oracle/_ref, compiled from the reference .cl) on
                       the host cores, bounded sample.  N=1, rank 0 only.
