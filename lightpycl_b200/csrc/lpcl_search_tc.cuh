@@ -29,8 +29,9 @@
 // Shared-memory operands use the no-swizzle K-major canonical layout (8-row x 16-byte core
 // matrices): element (row, k) at (k / 4) * rows * 16 + (row / 8) * 128 + (row % 8) * 16 + (k % 4) * 4.
 // The triangle tiles are stored in exactly that layout in global memory, so a tile is one 1-D TMA
-// bulk copy.  Measured pieces (tools/ubench_tmem.cu): tcgen05.ld sustains > 400 B/clk/SM, a
-// 128x256x8 tf32 MMA issues every 167 clk.
+// bulk copy.  Measured pieces (tools/ubench_tmem.cu, profiles/r1_tc_notes.txt): a 128 x N x 8 tf32
+// MMA takes N / 2 cycles (96 here; 4092 flop/clk/SM); tcgen05.ld moves ~43 B/clk per warp whatever
+// its shape (310-340 B/clk/SM with 8 warps) and does not contend with the MMAs.
 #pragma once
 
 #include "lpcl_search.cuh"

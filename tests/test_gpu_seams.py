@@ -315,7 +315,7 @@ def test_resolve_and_scatter_seams_on_random_inputs(seed):
         g.close()
 
 
-@pytest.mark.parametrize("seed,scale", [(0, 1.0), (1, 300.0), (2, 0.05)])
+@pytest.mark.parametrize("seed,scale", [(0, 1.0), (1, 300.0), (2, 0.05), (3, 3.0e4), (4, 2.0e-3)])
 def test_search_on_adversarial_triangle_soup(seed, scale):
     """The search (filter + exact re-evaluation + atomic merge) against the oracle on a random
     triangle soup with rays aimed AT edges, vertices and centroids, origins lying on other
@@ -385,4 +385,5 @@ def test_search_on_adversarial_triangle_soup(seed, scale):
             assert np.array_equal(util.bits(got[0]), util.bits(want[0])), "nearest t differs (%s R=%d)" % (impl, R)
     finally:
         g.close()
-    assert (want[1] > 0).mean() > 0.3 and (want[1] > 1).sum() > 100  # the soup really is hit, often more than once
+    # the soup really is hit, often more than once (tiny scenes lose hits to the reference's ABSOLUTE |DEN| < 1e-6 cut-off, Q7)
+    assert (want[1] > 0).mean() > (0.3 if scale >= 0.05 else 0.1) and (want[1] > 1).sum() > 100
