@@ -69,6 +69,11 @@ def sorted_sequential_sum_f32(p):
     return np.float32(np.cumsum(flat, dtype=np.float32)[-1])
 
 
+from .geo_optical_elements import GeoObject as _GeoObject  # noqa: E402
+
+_INDEXED_TRIBUF = _GeoObject.tribuf  # meshes whose tribuf() is the stock gather take the fast path below
+
+
 def flatten_meshes(meshes):
     """it:121-151.  Returns dict(v0, v1, v2 (T,4) f32, tri_mesh (T,) i32, mat_type i32, ior, refl, diss f32)."""
     m = len(meshes)
@@ -78,24 +83,45 @@ def flatten_meshes(meshes):
     ior = np.zeros(m, dtype=np.float32)
     refl = np.zeros(m, dtype=np.float32)
     diss = np.zeros(m, dtype=np.float32)
-    v0s, v1s, v2s, ids = [], [], [], []
+    parts = []  # (vertices f32 (V,4), triangles (T,3) int) for indexed meshes, else (v0, v1, v2) f32 arrays
+    total = 0
     for j, mesh in enumerate(meshes):
         mat = mesh.getMaterialBuf()
         mat_type[j] = np.int32(mat.get("type"))
         ior[j] = np.float32(mat.get("IOR"))
         refl[j] = np.float32(mat.get("R"))
         diss[j] = np.float32(mat.get("dissipation"))
-        tb = mesh.tribuf()
-        a = np.asarray(tb[0], dtype=np.float32).reshape(-1, 4)
-        if len(a) == 0:
+        verts, tris = getattr(mesh, "vertices", None), getattr(mesh, "triangles", None)
+        if verts is not None and tris is not None and type(mesh).tribuf is _INDEXED_TRIBUF:
+            # same values as tribuf() -> float32 (it:141-149): the cast commutes with the gather, and
+            # gathering float32 rows straight into the output skips three float64 temporaries per mesh
+            v = np.ascontiguousarray(np.asarray(verts, dtype=np.float32).reshape(-1, 4))
+            t = np.asarray(tris).reshape(-1, 3)
+            part, count = (v, t), len(t)
+        else:
+            tb = mesh.tribuf()
+            part = tuple(np.asarray(tb[k], dtype=np.float32).reshape(-1, 4) for k in range(3))
+            count = len(part[0])
+        if count == 0:
             raise ValueError("mesh %d has no triangles (the reference kernel requires non-empty meshes)" % j)
-        v0s.append(a)
-        v1s.append(np.asarray(tb[1], dtype=np.float32).reshape(-1, 4))
-        v2s.append(np.asarray(tb[2], dtype=np.float32).reshape(-1, 4))
-        ids.append(np.full(len(a), j, dtype=np.int32))
-    return dict(v0=np.ascontiguousarray(np.concatenate(v0s)), v1=np.ascontiguousarray(np.concatenate(v1s)),
-                v2=np.ascontiguousarray(np.concatenate(v2s)), tri_mesh=np.ascontiguousarray(np.concatenate(ids)),
-                mat_type=mat_type, ior=ior, refl=refl, diss=diss)
+        parts.append((part, count))
+        total += count
+    v0 = np.empty((total, 4), dtype=np.float32)
+    v1 = np.empty((total, 4), dtype=np.float32)
+    v2 = np.empty((total, 4), dtype=np.float32)
+    tri_mesh = np.empty(total, dtype=np.int32)
+    off = 0
+    for j, (part, count) in enumerate(parts):
+        sl = slice(off, off + count)
+        if len(part) == 2:
+            v, t = part
+            for k, out in enumerate((v0, v1, v2)):
+                np.take(v, t[:, k], axis=0, out=out[sl])
+        else:
+            v0[sl], v1[sl], v2[sl] = part
+        tri_mesh[sl] = j
+        off += count
+    return dict(v0=v0, v1=v1, v2=v2, tri_mesh=tri_mesh, mat_type=mat_type, ior=ior, refl=refl, diss=diss)
 
 
 # ------------------------------------------------------------------------------------------ device-side state
@@ -312,7 +338,11 @@ class CL_Tracer:
 
         # shard the rays over the ranks (contiguous blocks keep the reference order inside a rank)
         n_all = len(origin)
-        input_power = float(sorted_sequential_sum_f32(power))
+        # it:115 input power = sum(np.sort(power)), a sequential float32 sum over ALL rays: only the
+        # termination test needs it, so it is evaluated in run() while generation 0 is on the GPU
+        self._power_all = power
+        self._power_needs_allreduce = False
+        self.input_power = None
         lineage_base = 0
         pow_shape = None if power.ndim == 1 else power.shape
         if self.world_size > 1 and self.shard_input:
@@ -323,8 +353,7 @@ class CL_Tracer:
         elif self.world_size > 1:  # every rank brought its own rays
             counts = _dist.all_gather_int(len(origin), self._group, self.device)
             lineage_base = int(sum(counts[: self.rank]))
-            input_power = _dist.all_reduce_sum(input_power, self._group, self.device)
-        self.input_power = input_power
+            self._power_needs_allreduce = True
         self.timings["host_flatten_s"] = time() - t0
 
         t0 = time()
@@ -340,6 +369,16 @@ class CL_Tracer:
         self.h2d_bytes = int(sum(flat[k].nbytes for k in ("v0", "v1", "v2")) + n * (16 + 16 + 4))
         self.timings["upload_s"] = time() - t0
 
+    def _ensure_input_power(self):
+        """Total source power as the reference sums it (it:115); with rays brought per rank, summed
+        over the ranks (a collective: every rank calls this at the same point of run())."""
+        if self.input_power is None:
+            p = float(sorted_sequential_sum_f32(self._power_all))
+            if self._power_needs_allreduce:
+                p = _dist.all_reduce_sum(p, self._group, self.device)
+            self.input_power = p
+        return self.input_power
+
     def run(self, trace_iterations=100, trace_until_dissipated=0.99, max_ray_len=np.float32(1e3),
             ior_env=np.float32(1.0)):
         """The device-resident loop (replaces it:241-391).  Can be called repeatedly after one
@@ -350,7 +389,6 @@ class CL_Tracer:
         max_ray_len = np.float32(max_ray_len)
         ior_env = np.float32(ior_env)
         job = self._job
-        input_power = self.input_power
         pow_shape = job["pow_shape"]
         prof = self.profile
         events = []
@@ -423,6 +461,7 @@ class CL_Tracer:
                         events.append((n, ev))
                     self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
                     counters_host.copy_(counters_dev, non_blocking=True)
+                    self._ensure_input_power()  # host work hidden behind the kernels just launched
                     stream.synchronize()
                     sc = _cabi.StepCounters.from_buffer_copy(counters_host.numpy().tobytes())
                     c = {k: getattr(sc, k) for k, _ in _cabi.StepCounters._fields_}
@@ -446,6 +485,7 @@ class CL_Tracer:
                     self._measured_per_iter.append(0)
 
                 # it:372-391, evaluated over ALL ranks
+                input_power = self._ensure_input_power()
                 live, power_left = c["n_reflect"] + c["n_refract"], c["live_power"]
                 if self.world_size > 1:
                     live, power_left = _dist.all_reduce_pair(live, power_left, self._group, self.device)
@@ -493,10 +533,15 @@ class CL_Tracer:
         if self.world_size > 1 and gather:
             pos_pwr = _dist.gather_measured(pos_pwr, self._measured_lineage[: self._measured_count], per_iter,
                                             self._group, self.device)
-        rec = pos_pwr.cpu().numpy()
-        pos = np.ascontiguousarray(rec.copy())
-        pwr = np.ascontiguousarray(pos[:, 3].copy())
-        pos[:, 3] = 0.0
+        if pos_pwr.is_cuda:  # split (x, y, z, power) on the GPU: two device->host copies, no host passes
+            pwr_dev = pos_pwr[:, 3].contiguous()
+            pos_dev = pos_pwr.clone()
+            pos_dev[:, 3] = 0.0
+            pos, pwr = pos_dev.cpu().numpy(), pwr_dev.cpu().numpy()
+        else:
+            pos = np.ascontiguousarray(pos_pwr.numpy().copy())
+            pwr = np.ascontiguousarray(pos[:, 3].copy())
+            pos[:, 3] = 0.0
         if len(self._measured_per_iter) == 1 and self.results is not None and len(self.results._dev) == 1 \
                 and self.results._dev[0][2] is not None:
             pwr = pwr.reshape((-1,) + tuple(self.results._dev[0][2][1:]))  # it:406: no flatten for k == 0
