@@ -547,6 +547,63 @@ static void run_shapes()
     run_shape<16>(cyc, sink, sms); run_shape<32>(cyc, sink, sms); run_shape<64>(cyc, sink, sms); run_shape<128>(cyc, sink, sms);
 }
 
+// (A3) other tcgen05.ld shapes, 32 registers (4 KB per warp) per instruction
+template <int SHAPE> // 0: 32x32b.x32   1: 16x256b.x8   2: 16x128b.x16   3: 16x64b.x32
+__global__ void ldtm_shape2_kernel(unsigned long long *cycles, unsigned *sink, int iters)
+{
+    __shared__ uint32_t base_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc_512(&base_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = base_slot + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        uint32_t r[32];
+        const uint32_t a = base + (uint32_t)((i * 32) & 255);
+#define LD32(str) asm volatile(str " {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+                     : R8(r, 0), R8(r, 8), R8(r, 16), R8(r, 24) : "r"(a) : "memory")
+        if (SHAPE == 0) LD32("tcgen05.ld.sync.aligned.32x32b.x32.b32");
+        if (SHAPE == 1) LD32("tcgen05.ld.sync.aligned.16x256b.x8.b32");
+        if (SHAPE == 2) LD32("tcgen05.ld.sync.aligned.16x128b.x16.b32");
+        if (SHAPE == 3) LD32("tcgen05.ld.sync.aligned.16x64b.x32.b32");
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) acc ^= r[k] ^ r[k + 1] ^ r[k + 2] ^ r[k + 3];
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+    if (acc == 0x12345678u) sink[0] = acc;
+    __syncthreads();
+    if (warp == 0) tmem_free_512(base_slot);
+}
+template <int SHAPE>
+static void run_shape2(const char *name, unsigned long long *cyc, unsigned *sink, int sms)
+{
+    std::vector<unsigned long long> h(sms);
+    const int iters = 4096;
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        for (int rep = 0; rep < 2; ++rep) { ldtm_shape2_kernel<SHAPE><<<sms, warps * 32>>>(cyc, sink, iters); CK(cudaDeviceSynchronize()); }
+        CK(cudaMemcpy(h.data(), cyc, sms * 8, cudaMemcpyDeviceToHost));
+        double mean = 0; for (int i = 0; i < sms; ++i) mean += (double)h[i]; mean /= sms;
+        printf("ldtm %-12s warps %2d : %6.1f cycles per 4 KB load per warp  %6.1f B/clk/warp  %6.1f B/clk/SM\n", name, warps, mean / iters,
+               (double)iters * 4096 / mean, (double)iters * 4096 * warps / mean);
+    }
+}
+static void run_shapes2()
+{
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    unsigned long long *cyc; unsigned *sink;
+    CK(cudaMalloc(&cyc, sms * 8)); CK(cudaMalloc(&sink, 4));
+    run_shape2<0>("32x32b.x32", cyc, sink, sms); run_shape2<1>("16x256b.x8", cyc, sink, sms);
+    run_shape2<2>("16x128b.x16", cyc, sink, sms); run_shape2<3>("16x64b.x32", cyc, sink, sms);
+}
+
 int main(int argc, char **argv)
 {
     cudaDeviceProp p;
@@ -555,6 +612,7 @@ int main(int argc, char **argv)
     if (argc > 1 && !strcmp(argv[1], "mma")) run_mma();
     else if (argc > 1 && !strcmp(argv[1], "contention")) run_contention();
     else if (argc > 1 && !strcmp(argv[1], "shapes")) run_shapes();
+    else if (argc > 1 && !strcmp(argv[1], "shapes2")) run_shapes2();
     else run_ldtm();
     return 0;
 }
