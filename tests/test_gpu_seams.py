@@ -387,3 +387,48 @@ def test_search_on_adversarial_triangle_soup(seed, scale):
         g.close()
     # the soup really is hit, often more than once (tiny scenes lose hits to the reference's ABSOLUTE |DEN| < 1e-6 cut-off, Q7)
     assert (want[1] > 0).mean() > (0.3 if scale >= 0.05 else 0.1) and (want[1] > 1).sum() > 100
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_search_with_thousands_of_coincident_triangles(impl):
+    """Every ray crosses 3,000 copies of the same two triangles (plus a far plate in a second mesh):
+    3,000 exact-t ties per ray (the first triangle index must win, cl:278), crossing counts in the
+    thousands, and a candidate density that overflows the tensor-core kernel's per-warp queues, so
+    its in-place overflow evaluation runs too."""
+    rng = np.random.RandomState(11)
+    copies = 3000
+    quad = np.array([[[-1, -1, 5], [1, -1, 5], [1, 1, 5]], [[-1, -1, 5], [1, 1, 5], [-1, 1, 5]]], dtype=np.float64)
+    stack = np.tile(quad, (copies, 1, 1))                       # mesh 0: 6,000 triangles, pairwise coincident
+    plate = quad * np.array([3.0, 3.0, 1.0])
+    plate[:, :, 2] = 9.0                                        # mesh 1: two larger triangles further out
+    tris = np.concatenate((stack, plate))
+    T, M, n = len(tris), 2, 700
+
+    class Soup:
+        pass
+
+    sc = Soup()
+    pad = lambda a: np.ascontiguousarray(np.concatenate((a, np.zeros((len(a), 1))), axis=1), dtype=np.float32)
+    sc.v0, sc.v1, sc.v2 = pad(tris[:, 0]), pad(tris[:, 1]), pad(tris[:, 2])
+    sc.tri_mesh = np.concatenate((np.zeros(len(stack), np.int32), np.ones(len(plate), np.int32)))
+    sc.tri_count, sc.mesh_count = T, M
+    sc.mat_type, sc.ior = np.zeros(M, np.int32), np.ones(M, np.float32)
+    sc.refl, sc.diss = np.ones(M, np.float32), np.zeros(M, np.float32)
+    origin = pad(rng.uniform(-0.2, 0.2, (n, 3)))
+    target = np.concatenate((rng.uniform(-0.9, 0.9, (n, 2)), np.full((n, 1), 5.0)), axis=1)
+    d3 = target - origin[:, :3]
+    direc = pad(d3 / np.linalg.norm(d3, axis=1, keepdims=True))
+    max_ray_len = np.float32(100.0)
+
+    want = oracle.intersect(sc, origin, direc, max_ray_len, "port")
+    assert (want[1][:, 0] == copies).all() and (want[1][:, 1] == 1).all()     # every ray: 3,000 + 1 crossings
+    assert (want[2][:, 0] < 2).all()                                             # ties: the first copy wins
+    g = GpuSeams(sc)
+    _set_search(impl, 0, 0)
+    try:
+        got = g.intersect(origin, direc, max_ray_len)
+    finally:
+        _clear_search()
+        g.close()
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert np.array_equal(util.bits(got[0]), util.bits(want[0]))
