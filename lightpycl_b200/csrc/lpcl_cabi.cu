@@ -210,7 +210,10 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     build_filter_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d.v0, d.v1, d.v2, d.tiles, n_tiles, d.vmax,
                                                                             (float4 *)(base + off_filter));
     const long long tc_slots = (long long)tc_n_tiles * TC_TILE_TRIS;
-    build_tc_kernel<<<(unsigned)((tc_slots + 127) / 128), 128, 0, stream>>>(d.v0, d.v1, d.v2, d.tc_tiles, tc_n_tiles, d.vmax,
+    TileInfo *tc_tiles_dev = (TileInfo *)(base + off_tc_tiles);
+    tc_tile_vmax_kernel<<<(unsigned)((tc_slots + 127) / 128), 128, 0, stream>>>(d.v0, d.v1, d.v2, tc_tiles_dev, tc_n_tiles);
+    tc_tile_vmax_finish_kernel<<<(unsigned)((tc_n_tiles + 127) / 128), 128, 0, stream>>>(tc_tiles_dev, tc_n_tiles);
+    build_tc_kernel<<<(unsigned)((tc_slots + 127) / 128), 128, 0, stream>>>(d.v0, d.v1, d.v2, d.tc_tiles, tc_n_tiles,
                                                                            (float *)(base + off_tc_filter));
     SCENE_TRY(cudaGetLastError());
     for (int v = 0; v < kNumTcVariants; ++v)

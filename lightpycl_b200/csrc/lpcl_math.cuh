@@ -167,6 +167,27 @@ LPCL_HD float filter_ray_scale(V3 o, V3 d, float vmax)
     float f = L / (4.0f * vmax);
     return 1.2e-7f * d2 * L * (f > 1.0f ? f : 1.0f); // 2 * 2^-24 = 1.19e-7
 }
+// The same K2 with V = a bound of the vertex norms of ONE TILE of triangles (the derivation only
+// needs |V0| + Emax <= 2 V for the triangle at hand): the ray keeps |O| and 2 u |D|^2, the tile brings
+// 2 V and 1 / (4 V).  Used by the tensor-core search, whose tiles store their own bound - a scene
+// with a large far shell (a measure dome) no longer inflates the margin of its small inner triangles.
+struct RayScale {
+    float lo;   // |O|
+    float d2u;  // 1.2e-7 |D|^2
+};
+LPCL_HD RayScale filter_ray_parts(V3 o, V3 d)
+{
+    RayScale r;
+    r.lo = sqrtf(o.x * o.x + o.y * o.y + o.z * o.z);
+    r.d2u = 1.2e-7f * (d.x * d.x + d.y * d.y + d.z * d.z);
+    return r;
+}
+LPCL_HD float filter_ray_scale_tile(RayScale r, float two_v, float inv_four_v)
+{
+    float L = r.lo + two_v;
+    float f = L * inv_four_v;
+    return r.d2u * L * (f > 1.0f ? f : 1.0f);
+}
 
 // The filter for one (ray, triangle), operation by operation as the packed device loop evaluates
 // each lane (fma.rn.f32x2 == two fmaf).  Used by the host property test and by nothing on the GPU.

@@ -60,9 +60,36 @@ __host__ __device__ inline int tc_canon(int row, int k, int rows) // float index
     return (k >> 2) * rows * 4 + (row >> 3) * 32 + (row & 7) * 4 + (k & 3);
 }
 // ------------------------------------------------------------------------------------------ scene build
+// TileInfo.pad of a tensor-core tile = float bits of Vc, a bound of the vertex norms of ITS triangles:
+// the filter margin of the tile is built on Vc instead of the scene-wide Vmax (lpcl_math.cuh,
+// filter_ray_scale_tile).  Pass 1: max |v|^2 per tile (non-negative floats order as unsigned ints).
+__global__ void tc_tile_vmax_kernel(const float4 *v0, const float4 *v1, const float4 *v2, TileInfo *tiles, int n_tiles)
+{
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= (long long)n_tiles * TC_TILE_TRIS) return;
+    const int tile = (int)(slot / TC_TILE_TRIS), j = (int)(slot % TC_TILE_TRIS);
+    if (j >= tiles[tile].count) return;
+    const int t = tiles[tile].tri0 + j;
+    const float4 a = v0[t], b = v1[t], c = v2[t];
+    const float m = fmaxf(fmaxf(a.x * a.x + a.y * a.y + a.z * a.z, b.x * b.x + b.y * b.y + b.z * b.z),
+                          c.x * c.x + c.y * c.y + c.z * c.z);
+    if (m > 0.0f) atomicMax(reinterpret_cast<unsigned *>(&tiles[tile].pad), __float_as_uint(m));
+}
+// Pass 2: Vc = sqrt(max |v|^2) rounded up to a power of two (never zero): neighbouring tiles then
+// share their Vc, and the sweep rebuilds its per-ray margin constants only when Vc changes
+__global__ void tc_tile_vmax_finish_kernel(TileInfo *tiles, int n_tiles)
+{
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= n_tiles) return;
+    const float v = fmaxf(sqrtf(__int_as_float(tiles[tile].pad)) * 1.0001f, 1e-30f);
+    int e;
+    const float m = frexpf(v, &e); // v = m 2^e, 0.5 <= m < 1
+    tiles[tile].pad = __float_as_int(ldexpf(1.0f, m > 0.5f ? e : e - 1));
+}
+
 // one thread per (tile, triangle slot): three rows of 24 floats scattered into the canonical layout
 __global__ void build_tc_kernel(const float4 *v0, const float4 *v1, const float4 *v2, const TileInfo *tiles, int n_tiles,
-                                const float *vmax, float *out)
+                                float *out)
 {
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= (long long)n_tiles * TC_TILE_TRIS) return;
@@ -72,7 +99,7 @@ __global__ void build_tc_kernel(const float4 *v0, const float4 *v1, const float4
     TcRows r;
     if (j < ti.count) {
         float4 a = v0[ti.tri0 + j], b = v1[ti.tri0 + j], c = v2[ti.tri0 + j];
-        r = make_tc_rows(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), *vmax);
+        r = make_tc_rows(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), __int_as_float(ti.pad));
     } else { // padding: never read back (the epilogue stops at ti.count)
         for (int q = 0; q < 3; ++q)
             for (int k = 0; k < 6; ++k) r.c[q][k] = 0.0f;
@@ -272,17 +299,15 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     const int half = (warp >> 2) & 1;
     const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
     const float eps = eps_len(max_ray_len);
-    u64 k2[RT];
+    RayScale rs[RT]; // |O| and 2 u |D|^2 of this thread's ray in each ray tile: the margin constant K2 is rebuilt per triangle tile
     if (warp < TC_EPI_WARPS) {
-        const float vmax = *sc.vmax;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
             // a row beyond the last ray sweeps a copy of the last ray (its candidates are dropped)
             const long long i = min(ray0 + (long long)j * TC_M, rays.n - 1);
             const long long ph = rays.phys(i);
             const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
-            const float kk = filter_ray_scale(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), vmax);
-            k2[j] = pack2(__float_as_uint(kk), __float_as_uint(kk));
+            rs[j] = filter_ray_parts(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
             if ((j & 1) == half) {
                 const float a6[6] = {o.y * d.z - o.z * d.y, o.z * d.x - o.x * d.z, o.x * d.y - o.y * d.x, d.x, d.y, d.z};
                 float *dst = a_buf + j * TC_A_FLOATS;
@@ -393,13 +418,25 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             tc_ld_48(lane_addr + 48u, rB);
         }
         int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
+        u64 k2s[RT];
+        int vc_bits = 0; // Vc is a positive float: the first tile always differs
         for (int it = 0; it < nt; ++it) {
             const int4 ti4 = ti_next; // fetched one tile ahead: the L2 latency is off the critical path
             if (it + 1 < nt) ti_next = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it + 1));
             const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
+            if (ti4.w != vc_bits) { // K2 of (this thread's ray in each ray tile, tiles with this Vc): rebuilt when Vc changes
+                vc_bits = ti4.w;
+                const float two_vc = 2.0f * __int_as_float(vc_bits), inv_four_vc = __frcp_rn(4.0f * __int_as_float(vc_bits));
+#pragma unroll
+                for (int j = 0; j < RT; ++j) {
+                    const float kk = filter_ray_scale_tile(rs[j], two_vc, inv_four_vc);
+                    k2s[j] = pack2(__float_as_uint(kk), __float_as_uint(kk));
+                }
+            }
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
                 const int g = it * RT + j, buf = g & 1;
+                const u64 k2 = k2s[j];
                 const bool more = g + 1 < steps;
                 const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
                 const long long i = ray0 + (long long)j * TC_M;
@@ -409,13 +446,13 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 if (j == 0 && *(volatile int *)q_count >= TC_QUEUE_DRAIN) // once per triangle tile; an overflowing append evaluates in place
                     tc_drain(queue, q_count, sc, rays, eps, key, cnt);
-                test_chunk(rA, k2[j], chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                test_chunk(rA, k2, chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
                 if (more) { // the first chunk of step g + 1 loads while the second chunk of step g is tested
                     mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
                     tc_fence_after();
                     tc_ld_48(next_addr, rA);
                 }
-                test_chunk(rB, k2[j], (chunk0 + 1) * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                test_chunk(rB, k2, (chunk0 + 1) * TC_CHUNK_TRIS, tri0, count, mesh, i);
                 if (more) tc_ld_48(next_addr + 48u, rB);
             }
         }

@@ -52,7 +52,11 @@ static long property(int tc, long n, unsigned seed, double scene_radius, double 
         float k2 = filter_ray_scale(o, d, vmax);
         bool cand;
         if (tc) { // tensor-core model: a candidate under every admissible rounding of the three GEMM outputs
-            TcRows q = make_tc_rows(a, b, c, vmax);
+            // the tile-local vertex-norm bound: anything from this triangle's own largest vertex norm upwards
+            float na = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), nb = sqrtf(b.x * b.x + b.y * b.y + b.z * b.z), nc = sqrtf(c.x * c.x + c.y * c.y + c.z * c.z);
+            float vloc = fmaxf(fmaxf(na, nb), fmaxf(nc, 1e-30f)) * 1.0001f * (float)(1.0 + (rnd() < 0.5 ? 0.0 : 3.0 * rnd()));
+            k2 = filter_ray_scale_tile(filter_ray_parts(o, d), 2.0f * vloc, 1.0f / (4.0f * vloc));
+            TcRows q = make_tc_rows(a, b, c, vloc);
             cand = true;
             for (int push = 0; push < 8; ++push) cand = cand && filter_candidate_tc(q, d.x, d.y, d.z, mx, my, mz, k2, push);
         } else {
