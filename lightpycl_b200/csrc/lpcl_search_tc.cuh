@@ -397,12 +397,14 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 none[(2 * q + 1) & 3] = or_and(hi32(du[q]), hi32(dv[q]), none[(2 * q + 1) & 3]);
             }
             if ((int)(none[0] & none[1] & none[2] & none[3]) >= 0) { // rare: a triangle of the chunk passed both tests
-                unsigned mask = 0;
+                // sign bits (1 = failed) funnel-shifted in from triangle 15 down to 0: bit t of `failed` = triangle t
+                unsigned failed = 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    mask |= ((~(lo32(du[q]) | lo32(dv[q]))) >> 31) << (2 * q);
-                    mask |= ((~(hi32(du[q]) | hi32(dv[q]))) >> 31) << (2 * q + 1);
+                for (int q = 7; q >= 0; --q) {
+                    failed = __funnelshift_l(hi32(du[q]) | hi32(dv[q]), failed, 1);
+                    failed = __funnelshift_l(lo32(du[q]) | lo32(dv[q]), failed, 1);
                 }
+                unsigned mask = ~failed & 0xffffu;
                 const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
                 if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
                 n_cand += __popc(mask);
