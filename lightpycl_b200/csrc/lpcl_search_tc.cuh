@@ -184,7 +184,7 @@ __device__ __forceinline__ void tc_ld_48(uint32_t taddr, uint32_t *r)
 // with atomicAdd / atomicMin; the packed key (t bits, triangle) reproduces "first triangle index
 // wins ties" (cl:278) whatever the evaluation order.
 constexpr int TC_QUEUE_CAP = 256;   // records per warp
-constexpr int TC_QUEUE_DRAIN = 128; // drain threshold, checked once per accumulator
+constexpr int TC_QUEUE_DRAIN = 128; // drain threshold, checked once per triangle tile
 
 __device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &rays, long long i, int tri, int mesh, float eps,
                                              unsigned long long *key, int *cnt)
@@ -250,7 +250,6 @@ __device__ __forceinline__ void tc_enqueue(unsigned mask, int tri_base, long lon
 }
 
 // ------------------------------------------------------------------------------------------ the sweep
-constexpr int tc_queue_bytes() { return TC_EPI_WARPS * (TC_QUEUE_CAP * 16 + 16); }
 __host__ __device__ constexpr int tc_smem_bytes(int rt)
 {
     // padded past half an SM so that two CTAs (two 512-column TMEM allocations) never share an SM
