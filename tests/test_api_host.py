@@ -127,3 +127,34 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_flatten_fast_path_equals_tribuf_path():
+    """flatten_meshes gathers indexed meshes (stock GeoObject.tribuf) straight into float32 buffers;
+    duck-typed meshes go through tribuf().  Both must give the same bits (cast commutes with gather),
+    also after rotate/translate and for float64 cube vertices (geo:154-162)."""
+    from lightpycl_b200 import geo_optical_elements as goe
+    from lightpycl_b200 import scenes
+    from lightpycl_b200.iterative_tracer import flatten_meshes
+
+    _, meshes, _ = scenes.nested_cubes(ray_count=4)
+    _, more, _ = scenes.directivity_lens(ray_count=4)
+    meshes = list(meshes) + list(more)
+    meshes[1].rotate(axis="x", angle=0.3, pivot=(0, 0, 0, 0))
+
+    class Duck:  # same data, but only the reference's duck-typed interface (it:130,137)
+        def __init__(self, m):
+            self._m = m
+
+        def getMaterialBuf(self):
+            return self._m.getMaterialBuf()
+
+        def tribuf(self):
+            return goe.GeoObject.tribuf(self._m)
+
+    fast, slow = flatten_meshes(meshes), flatten_meshes([Duck(m) for m in meshes])
+    for k in ("v0", "v1", "v2"):
+        assert fast[k].dtype == np.float32 and fast[k].flags["C_CONTIGUOUS"]
+        assert np.array_equal(fast[k].view(np.uint32), slow[k].view(np.uint32)), k
+    for k in ("tri_mesh", "mat_type", "ior", "refl", "diss"):
+        assert np.array_equal(fast[k], slow[k]), k
