@@ -362,9 +362,11 @@ class CL_Tracer:
             n = len(origin)
             job = dict(n=n, lineage_base=lineage_base, pow_shape=pow_shape)
             if n > 0:
-                job["origin"] = torch.from_numpy(np.ascontiguousarray(origin)).to(self.device)
-                job["dir"] = torch.from_numpy(np.ascontiguousarray(direc)).to(self.device)
-                job["power"] = torch.from_numpy(np.ascontiguousarray(power.reshape(-1))).to(self.device)
+                # page-locked source arrays (light_source pins them when CUDA is present) go by direct DMA;
+                # the host arrays stay referenced by the job until run() has synchronised
+                host = [torch.from_numpy(np.ascontiguousarray(a)) for a in (origin, direc, power.reshape(-1))]
+                job["host"] = host
+                job["origin"], job["dir"], job["power"] = (h.to(self.device, non_blocking=h.is_pinned()) for h in host)
             self._job = job
         self.h2d_bytes = int(sum(flat[k].nbytes for k in ("v0", "v1", "v2")) + n * (16 + 16 + 4))
         self.timings["upload_s"] = time() - t0

@@ -32,6 +32,27 @@ def _Rz(a):
     return np.array([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]], dtype=np.float64)
 
 
+def _pinned(a):
+    """The same float32 values in page-locked host memory when a CUDA device is present, so that the
+    tracer's host->device copy of the rays is a direct DMA (pageable memory is staged at ~1/4 of the
+    rate).  A no-op without CUDA or with LPCL_PIN_SOURCES=0; the array keeps its owner alive."""
+    import os
+
+    if os.environ.get("LPCL_PIN_SOURCES", "1") == "0" or a is None:
+        return a
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return a
+        a = np.ascontiguousarray(a)
+        if a.dtype != np.float32 or a.size == 0:
+            return a
+        return torch.from_numpy(a).pin_memory().numpy()
+    except Exception:  # no torch / no driver: plain NumPy arrays, as the reference has them
+        return a
+
+
 class light_source:
     """A point-like emitter with a directivity pattern (reference ls:28-43).
 
@@ -101,6 +122,10 @@ class light_source:
 
         rd = np.dot(rd, _Rx(elevation0))
         self.rays_dir = np.dot(rd, _Rz(azimuth0)).astype(np.float32)
+        self._pin_rays()
+
+    def _pin_rays(self):
+        self.rays_origin, self.rays_dir, self.rays_power = _pinned(self.rays_origin), _pinned(self.rays_dir), _pinned(self.rays_power)
 
     def random_collimated_rays(self, diameter=1.0):
         """Parallel rays from a random SQUARE footprint of side ``diameter`` (reference
@@ -125,6 +150,7 @@ class light_source:
 
         rays_dir = np.dot(rays_dir, _Rx(elevation0))
         self.rays_dir = np.array(np.dot(rays_dir, _Rz(azimuth0))).astype(np.float32)
+        self._pin_rays()
 
     def grid_rays(self):
         """Regular elevation x azimuth grid (reference ls:45-95).  The reference version no
@@ -157,6 +183,7 @@ class light_source:
         piv = np.array(pivot)
         self.rays_origin = np.array(np.add(np.dot(np.subtract(self.rays_origin, piv), R), piv)).astype(np.float32)
         self.rays_dir = np.array(np.dot(self.rays_dir, R)).astype(np.float32)
+        self._pin_rays()
 
     def save_dxf(self, dxf_file):
         """reference ls:191-204 (needs ``dxfwrite``); here a dependency-free ASCII DXF with one
