@@ -158,3 +158,30 @@ def test_flatten_fast_path_equals_tribuf_path():
         assert np.array_equal(fast[k].view(np.uint32), slow[k].view(np.uint32)), k
     for k in ("tri_mesh", "mat_type", "ior", "refl", "diss"):
         assert np.array_equal(fast[k], slow[k]), k
+
+
+def test_measured_result_buffers_are_reused_only_when_dropped():
+    """get_measured_rays hands out arrays backed by a small pool (first-touch page faults of fresh host
+    memory cost more than the copy): a backing buffer may be reused only when the caller holds no view
+    of it any more - results already handed out must never be overwritten."""
+    from lightpycl_b200.iterative_tracer import CL_Tracer
+
+    class Holder:  # the pool only needs an attribute dict
+        _host_array = CL_Tracer._host_array
+
+    t = Holder()
+    take = CL_Tracer._host_result_arrays
+    a, b = take(t, 1000)
+    a[:] = 1.0
+    a2, b2 = take(t, 900)                       # a, b still referenced: different memory
+    assert not np.shares_memory(a, a2) and not np.shares_memory(b, b2)
+    del a, b
+    a3, b3 = take(t, 800)                       # first set dropped: reused
+    pos_pool = t._host_pool[("pos", 4, np.dtype(np.float32).str)]
+    assert a3.base is pos_pool[0] and len(pos_pool) == 2
+    keep = a3[:10]                              # a view of a view still protects the buffer
+    del a3, b3
+    a4, _ = take(t, 700)
+    assert not np.shares_memory(keep, a4)
+    big, _ = take(t, 5000)                      # larger than any pooled buffer: a new one
+    assert big.shape == (5000, 4) and big.dtype == np.float32
