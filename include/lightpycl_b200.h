@@ -118,10 +118,14 @@ int lpcl_reflect_refract_rays(const lpcl_scene *scene, const float *d_origin, co
  *   org_pow  (cap,4) f32 : origin.xyz, w = power
  *   dir_prev (cap,4) f32 : direction.xyz, w = int32 bits of the previous hit-surface mesh id
  *                          (-2 for rays fresh from a source; reference it:118,344,373)
- *   lineage  (cap,) u64  : optional (may be NULL): (path << 32) | source_ray_index, where bit k of
- *                          `path` is set when the ray took the REFRACTED branch at iteration k
- *                          (k < 31, so the id stays positive as int64).  Sorting a generation by
- *                          lineage gives the reference order.
+ *   lineage  (cap,) u64  : optional (may be NULL): (path << 32) | index, where bit k of `path` is set
+ *                          when the ray took the REFRACTED branch at iteration k of the current
+ *                          lineage epoch (k < 31, so the id stays positive as int64).  Sorting a
+ *                          generation by lineage gives the reference order.  `index` is the source
+ *                          ray index in the first epoch; before the 31 branch bits run out the
+ *                          caller starts a new epoch by renumbering the live rays 0..n-1 in
+ *                          generation order (lightpycl_b200/dist.py renumber_lineage) and passes
+ *                          iteration numbers relative to the epoch start.
  * A generation of n rays is stored in two segments: logical ray i lives at physical index i for
  * i < seg_split, and at seg_base + (i - seg_split) otherwise.  (Generation 0: seg_split = n.)
  *
@@ -131,14 +135,19 @@ int lpcl_reflect_refract_rays(const lpcl_scene *scene, const float *d_origin, co
  *   parent power is rewritten in place in org_pow.w when the ray crossed a dissipative medium.
  * Children (surviving ones only, reference it:366-373) go to the next generation's buffers:
  *   reflected survivors, parent order kept, at [0, n_reflect); refracted survivors at
- *   [n, n + n_refract).  The next generation is therefore (seg_split = n_reflect, seg_base = n).
- *   Capacity needed: 2 n rays.
+ *   [children->seg_base, children->seg_base + n_refract), seg_base >= n.  With seg_base = n the next
+ *   generation is (seg_split = n_reflect, seg_base = n); capacity needed: seg_base + n rays.
+ *   A generation may also be processed in RAY TILES (the reference's <= 50,000-ray partitions,
+ *   it:218-273): call the step on consecutive logical ranges of the parents (pointers advanced, see
+ *   lightpycl_b200/iterative_tracer.py _Generation.c_struct) with the children pointers advanced by the
+ *   reflected survivors so far and seg_base = N + refracted so far - reflected so far; the tiles'
+ *   outputs then form the same two segments an untiled step writes, bit for bit.
  * Measured parents are appended, in ray order, as (dest.xyz, power) records to d_measured_out
  *   starting at record `measured_base` (reference get_measured_rays, it:395-411); when both
  *   parents->d_lineage and d_measured_lineage are given, the parent's lineage is stored alongside
  *   (used to merge the per-GPU buffers of a ray-sharded run back into the reference order).
  * d_counters receives the totals (read it after synchronising the stream).
- * d_workspace: lpcl_step_workspace_bytes(scene, n) bytes of device scratch (zeroed by the call).
+ * d_workspace: lpcl_step_workspace_bytes(scene, n) bytes of device scratch (initialised by the call).
  */
 typedef struct lpcl_step_counters {
     int64_t n_reflect;      /* surviving reflected children */
@@ -169,10 +178,11 @@ int lpcl_trace_step(const lpcl_scene *scene, const lpcl_generation *parents, con
                     void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream);
 
 /* The two halves of lpcl_trace_step, callable separately so the caller can put events between
- * them: lpcl_trace_search runs the nearest-hit search into d_workspace (adds to
- * d_counters->candidates when d_counters != NULL; does not zero it); lpcl_trace_resolve runs the
- * fused media-resolution / Fresnel / compaction kernel on that workspace (accumulates into
- * d_counters, which the caller zeroes).  lpcl_trace_step == zero counters + search + resolve. */
+ * them: lpcl_trace_search initialises d_workspace, ZEROES *d_counters (when != NULL), runs the
+ * nearest-hit search into the workspace and adds its candidate count to d_counters->candidates;
+ * lpcl_trace_resolve runs the fused media-resolution / Fresnel / compaction kernel on the workspace
+ * lpcl_trace_search just filled for the same parents and accumulates into d_counters.
+ * lpcl_trace_step == search + resolve: three kernel launches, no memsets. */
 int lpcl_trace_search(const lpcl_scene *scene, const lpcl_generation *parents, void *d_workspace,
                       float max_ray_len, lpcl_step_counters *d_counters, void *stream);
 int lpcl_trace_resolve(const lpcl_scene *scene, const lpcl_generation *parents, const lpcl_generation *children,

@@ -11,6 +11,7 @@
 
 #include "../../include/lightpycl_b200.h"
 #include "lpcl_material.cuh"
+#include "lpcl_search_exact.cuh"
 #include "lpcl_search_tc.cuh"
 
 using namespace lpcl;
@@ -274,7 +275,7 @@ static int64_t step_blocks(int64_t n) { return (n + STEP_RAYS - 1) / STEP_RAYS; 
 extern "C" int64_t lpcl_step_workspace_bytes(const lpcl_scene *s, int64_t n)
 {
     if (!s || n < 0) return 0;
-    return lpcl_scratch_bytes(s, n) + align_up(step_blocks(n) * 16 + 16, 256) + 256;
+    return lpcl_scratch_bytes(s, n) + align_up(step_blocks(n) * 16 + 16, 256) + 256; // scratch | scan_bytes(n) | slack
 }
 
 // LPCL_SEARCH_R / LPCL_SEARCH_THREADS / LPCL_SEARCH_CHUNKS override the launch heuristics without rebuilding.
@@ -284,8 +285,10 @@ static int env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
+// zero_a / zero_b: optional 64-bit-word areas cleared by the scratch initialisation launch
 static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray_len, void *d_scratch,
-                         unsigned long long *cand_total, cudaStream_t stream)
+                         unsigned long long *cand_total, cudaStream_t stream, unsigned long long *zero_a = nullptr,
+                         long long words_a = 0, unsigned long long *zero_b = nullptr, long long words_b = 0)
 {
     const int64_t n = rays.n;
     unsigned long long *key = (unsigned long long *)d_scratch;
@@ -296,11 +299,27 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
     {
         long long blocks = (total + 255) / 256;
         if (blocks > (long long)s->sm_count * 32) blocks = (long long)s->sm_count * 32;
-        scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key);
+        scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key, zero_a, words_a, zero_b, words_b);
     }
     // Default: the filter on the tensor cores (lpcl_search_tc.cuh).  LPCL_SEARCH_IMPL=simt selects the
     // packed-FP32 filter (lpcl_search.cuh) - kept as the second implementation the tests cross-check.
     const char *impl = getenv("LPCL_SEARCH_IMPL");
+    if (impl && strcmp(impl, "exact") == 0) {
+        // no filter at all: every pair takes the exact evaluation (lpcl_search_exact.cuh) - the on-GPU
+        // yardstick of the full-size parity tests, ~3x slower than the filtered searches
+        const int64_t ray_blocks = (n + EXACT_THREADS - 1) / EXACT_THREADS;
+        int64_t chunks = env_int("LPCL_SEARCH_CHUNKS", 0);
+        if (chunks <= 0) chunks = (32 * (int64_t)s->sm_count + ray_blocks - 1) / ray_blocks;
+        if (chunks < 1) chunks = 1;
+        if (chunks > s->dev.n_tiles) chunks = s->dev.n_tiles;
+        if (chunks > 65535) chunks = 65535;
+        int tiles_per_chunk = (int)((s->dev.n_tiles + chunks - 1) / chunks);
+        chunks = (s->dev.n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
+        search_exact_kernel<<<grid, EXACT_THREADS, 0, stream>>>(s->dev, rays, max_ray_len, key, cnt, tiles_per_chunk, cand_total);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (!impl || strcmp(impl, "simt") != 0) {
         const int want_rt = env_int("LPCL_SEARCH_RT", 0);
         int v = -1;
@@ -469,14 +488,21 @@ extern "C" int lpcl_pack_rays(const float *d_origin, const float *d_dir, const f
     return 0;
 }
 
+static int64_t scan_bytes(int64_t n) { return align_up(step_blocks(n) * 16 + 16, 256); }
+
 extern "C" int lpcl_trace_search(const lpcl_scene *s, const lpcl_generation *parents, void *d_workspace,
                                  float max_ray_len, lpcl_step_counters *d_counters, void *stream_)
 {
     if (!s || !d_workspace) return fail(LPCL_E_NULL, "lpcl_trace_search: NULL argument");
     int rc = check_gen(parents, "lpcl_trace_search(parents)", true);
     if (rc) return rc;
+    // the scratch initialisation also clears the counters and the look-back words lpcl_trace_resolve
+    // scans with: one generation = 3 launches (init, search, step), no memsets
+    char *scan = (char *)d_workspace + lpcl_scratch_bytes(s, parents->n);
     return launch_search(s, to_dev(parents), max_ray_len, d_workspace,
-                         d_counters ? (unsigned long long *)&d_counters->candidates : nullptr, (cudaStream_t)stream_);
+                         d_counters ? (unsigned long long *)&d_counters->candidates : nullptr, (cudaStream_t)stream_,
+                         (unsigned long long *)d_counters, d_counters ? (long long)(sizeof(lpcl_step_counters) / 8) : 0,
+                         (unsigned long long *)scan, scan_bytes(parents->n) / 8);
 }
 
 extern "C" int lpcl_trace_resolve(const lpcl_scene *s, const lpcl_generation *parents, const lpcl_generation *children,
@@ -491,8 +517,10 @@ extern "C" int lpcl_trace_resolve(const lpcl_scene *s, const lpcl_generation *pa
     rc = check_gen(children, "lpcl_trace_resolve(children)", false);
     if (rc) return rc;
     const int64_t n = parents->n;
-    if (children->capacity < 2 * n) return fail(LPCL_E_RANGE, "lpcl_trace_resolve: children capacity %lld < 2n = %lld",
-                                                (long long)children->capacity, (long long)(2 * n));
+    // children: reflected survivors fill [0, n_reflect), refracted ones [seg_base, seg_base + n_refract); both counts <= n
+    if (children->seg_base < n || children->capacity < children->seg_base + n)
+        return fail(LPCL_E_RANGE, "lpcl_trace_resolve: children need seg_base >= n and capacity >= seg_base + n (n = %lld, "
+                    "seg_base = %lld, capacity = %lld)", (long long)n, (long long)children->seg_base, (long long)children->capacity);
     if (d_measured_out && measured_capacity < measured_base + n)
         return fail(LPCL_E_RANGE, "lpcl_trace_resolve: measured buffer too small (%lld < %lld)",
                     (long long)measured_capacity, (long long)(measured_base + n));
@@ -503,9 +531,7 @@ extern "C" int lpcl_trace_resolve(const lpcl_scene *s, const lpcl_generation *pa
     char *ws = (char *)d_workspace;
     const unsigned long long *key = (const unsigned long long *)ws;
     const int *cnt = (const int *)(ws + scratch_key_bytes(s, n));
-    char *scan = ws + lpcl_scratch_bytes(s, n);
-    const int64_t scan_bytes = align_up(step_blocks(n) * 16 + 16, 256);
-    CUDA_TRY(cudaMemsetAsync(scan, 0, (size_t)scan_bytes, stream));
+    char *scan = ws + lpcl_scratch_bytes(s, n); // cleared by lpcl_trace_search
     unsigned long long *words = (unsigned long long *)(scan + 16); // two look-back status words per block
     step_kernel<<<(unsigned)step_blocks(n), STEP_THREADS, 0, stream>>>(
         s->dev, par, chi, key, cnt, (float4 *)d_dest_meas, (int4 *)d_hit, (float4 *)d_measured_out,
@@ -521,7 +547,6 @@ extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *paren
                                void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream_)
 {
     if (!d_counters) return fail(LPCL_E_NULL, "lpcl_trace_step: NULL counters");
-    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(lpcl_step_counters), (cudaStream_t)stream_));
     int rc = lpcl_trace_search(s, parents, d_workspace, max_ray_len, d_counters, stream_);
     if (rc) return rc;
     return lpcl_trace_resolve(s, parents, children, d_dest_meas, d_hit, d_measured_out, d_measured_lineage,

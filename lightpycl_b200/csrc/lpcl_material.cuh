@@ -363,8 +363,8 @@ step_kernel(SceneDev sc, RaysDev par, RaysDev chi, const unsigned long long *__r
             chi.dir_prev[c] = make_float4(it[k].rdir.x, it[k].rdir.y, it[k].rdir.z, __int_as_float(it[k].hit_mesh));
             if (chi.lineage) chi.lineage[c] = it[k].lin;
         }
-        if (bits & 2u) { // refracted survivors: second segment, starting at physical index n
-            const long long c = n + base_t + s_off[1][slot] + ((bits >> 16) & 0xffu);
+        if (bits & 2u) { // refracted survivors: second segment, starting at physical index chi.base (= n for a whole generation)
+            const long long c = chi.base + base_t + s_off[1][slot] + ((bits >> 16) & 0xffu);
             chi.org_pow[c] = make_float4(it[k].end.x, it[k].end.y, it[k].end.z, it[k].tpow);
             chi.dir_prev[c] = make_float4(it[k].tdir.x, it[k].tdir.y, it[k].tdir.z, __int_as_float(it[k].hit_mesh));
             if (chi.lineage) chi.lineage[c] = (iteration < 31) ? (it[k].lin | (1ull << (32 + iteration))) : it[k].lin;

@@ -163,10 +163,16 @@ __global__ void build_filter_kernel(const float4 *v0, const float4 *v1, const fl
 }
 
 // ------------------------------------------------------------------------------------------ scratch
-__global__ void scratch_init_kernel(unsigned long long *key, int *cnt, long long total, unsigned long long init_key)
+// Also clears up to two small 64-bit-word areas (the step counters and the look-back words of the
+// step kernel's chained scan), so that one generation needs no separate memset launches.
+__global__ void scratch_init_kernel(unsigned long long *key, int *cnt, long long total, unsigned long long init_key,
+                                    unsigned long long *zero_a, long long words_a, unsigned long long *zero_b,
+                                    long long words_b)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = i; k < words_a; k += stride) zero_a[k] = 0ull;
+    for (long long k = i; k < words_b; k += stride) zero_b[k] = 0ull;
     for (; i < total; i += stride) {
         key[i] = init_key;
         cnt[i] = 0;

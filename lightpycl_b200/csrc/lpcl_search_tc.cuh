@@ -186,7 +186,12 @@ __device__ __forceinline__ void tc_ld_48(uint32_t taddr, uint32_t *r)
 constexpr int TC_QUEUE_CAP = 256;   // records per warp
 constexpr int TC_QUEUE_DRAIN = 128; // drain threshold, checked once per triangle tile
 
-__device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &rays, long long i, int tri, int mesh, float eps,
+struct ExactLimits {
+    float eps;          // EPSILON = (float)(1e-6 * (double)max_ray_len): hits at t <= eps are ignored (cl:277)
+    float max_ray_len;  // hits at t >= max_ray_len are COUNTED but never become the nearest one (cl:252,278)
+};
+
+__device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &rays, long long i, int tri, int mesh, ExactLimits lim,
                                              unsigned long long *key, int *cnt)
 {
     const long long ph = rays.phys(i);
@@ -194,15 +199,17 @@ __device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &
     const float4 a = __ldg(sc.v0 + tri), b = __ldg(sc.v1 + tri), c = __ldg(sc.v2 + tri);
     float t;
     if (ray_triangle_exact(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t) &&
-        t > eps) {
+        t > lim.eps) {
         const long long slot = (long long)mesh * rays.n + i;
         atomicAdd(&cnt[slot], 1);
-        atomicMin(&key[slot], pack_key(t, tri));
+        // strict '<' against the running minimum that starts at max_ray_len (cl:278): t == max_ray_len must not
+        // replace the initial key even though its packed (t, triangle) value is smaller than (max_ray_len, -1)
+        if (t < lim.max_ray_len) atomicMin(&key[slot], pack_key(t, tri));
     }
 }
 
 // warp-collective
-__device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev &sc, const RaysDev &rays, float eps,
+__device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev &sc, const RaysDev &rays, ExactLimits eps,
                                       unsigned long long *key, int *cnt)
 {
     __syncwarp();
@@ -222,7 +229,7 @@ __device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev 
 
 // queue full (pathological candidate density): evaluate in place
 __device__ __noinline__ void tc_overflow(unsigned mask, int tri_base, long long i, int mesh, const SceneDev &sc,
-                                         const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
+                                         const RaysDev &rays, ExactLimits eps, unsigned long long *key, int *cnt)
 {
     while (mask) {
         const int b = __ffs((int)mask) - 1;
@@ -233,7 +240,7 @@ __device__ __noinline__ void tc_overflow(unsigned mask, int tri_base, long long 
 
 // one lane, inside the divergent rare branch: mask bit b = triangle tri_base + b passed the filter
 __device__ __forceinline__ void tc_enqueue(unsigned mask, int tri_base, long long i, int mesh, int4 *queue, int *q_count,
-                                           const SceneDev &sc, const RaysDev &rays, float eps, unsigned long long *key, int *cnt)
+                                           const SceneDev &sc, const RaysDev &rays, ExactLimits eps, unsigned long long *key, int *cnt)
 {
     const int c = __popc(mask);
     const int pos = atomicAdd(q_count, c);
@@ -297,7 +304,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     const int row = (warp & 3) * 32 + lane; // TMEM lane == ray row of every ray tile
     const int half = (warp >> 2) & 1;
     const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
-    const float eps = eps_len(max_ray_len);
+    const ExactLimits eps = {eps_len(max_ray_len), max_ray_len};
     RayScale rs[RT]; // |O| and 2 u |D|^2 of this thread's ray in each ray tile: the margin constant K2 is rebuilt per triangle tile
     if (warp < TC_EPI_WARPS) {
 #pragma unroll

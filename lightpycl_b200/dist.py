@@ -10,7 +10,12 @@ independent.  Here the ray axis is sharded over one process per GPU:
     global termination tests (it:372-391) - 16 bytes, latency bound;
   * at the end ONE padded all-gather of the measured records (x, y, z, power) + lineage
     implements ``get_measured_rays`` (it:395-411); merging by (iteration, lineage) restores the
-    reference's order, so 1/2/4/8-GPU runs return identical arrays.
+    reference's order, so 1/2/4/8-GPU runs return identical arrays;
+  * the 64-bit lineage holds PATH_BITS branch bits above a 32-bit index.  Before they run out
+    (every PATH_BITS iterations) ``renumber_lineage`` replaces every live ray's id by its rank in
+    the generation's global reference order (one all-gather of the live ids) and the branch bits
+    start over - traces of any depth keep the reference order (reference default: 100 iterations,
+    it:77).
 
 All helpers work on CPU tensors with the ``gloo`` backend too (used by the CPU tests).
 """
@@ -55,6 +60,9 @@ def _comm_device(group, device):
     return torch.device(device) if "nccl" in backend else torch.device("cpu")
 
 
+PATH_BITS = 31  # branch bits of a 64-bit lineage: id = (path << 32) | index, bit k of path = "refracted at epoch iteration k"
+
+
 def shard_bounds(n, world_size, rank):
     """Contiguous block [lo, hi) of rank ``rank`` out of ``n`` rays (sizes differ by at most 1)."""
     return (n * rank) // world_size, (n * (rank + 1)) // world_size
@@ -93,6 +101,38 @@ def all_reduce_pair(live, power, group, device):
     t = torch.tensor([float(live), float(power)], dtype=torch.float64, device=_comm_device(group, device))
     td.all_reduce(t, op=td.ReduceOp.SUM, group=_pg(group))
     return int(round(t[0].item())), float(t[1].item())
+
+
+def renumber_lineage(keys, group, device):
+    """Start a new lineage epoch: replace every live ray's id by its rank in the GLOBAL reference
+    order of the current generation (a dense index < 2^32, branch bits cleared).
+
+    ``keys``: this rank's ids in its local order.  Inside one generation the reference order is the
+    ascending id order and a rank's rays keep it (the compaction is order preserving), so ``keys`` is
+    strictly increasing and the global rank of a ray is its local index plus, for every other rank,
+    the number of that rank's ids below it - one padded all-gather and world_size searches.
+    Collective: every rank of the group calls it at the same iteration, also with zero rays."""
+    n = int(keys.shape[0])
+    if group is None:
+        return torch.arange(n, dtype=torch.int64, device=keys.device)
+    td = _td()
+    ws, rank = world(group)
+    dev = _comm_device(group, device)
+    counts = all_gather_int(n, group, device)
+    if sum(counts) >= (1 << 32):
+        raise ValueError("lineage renumbering needs < 2^32 live rays in a generation (got %d)" % sum(counts))
+    kmax = max(max(counts), 1)
+    mine = torch.full((kmax,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+    local = keys.to(dev)
+    if n:
+        mine[:n] = local
+    everyone = [torch.empty_like(mine) for _ in range(ws)]
+    td.all_gather(everyone, mine, group=_pg(group))
+    new = torch.arange(n, dtype=torch.int64, device=dev)
+    for r in range(ws):
+        if r != rank and counts[r] and n:
+            new += torch.searchsorted(everyone[r][: counts[r]], local)
+    return new.to(keys.device)
 
 
 def merge_measured(records, lineages, iter_ids):

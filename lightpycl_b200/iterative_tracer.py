@@ -22,6 +22,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import pickle
+import weakref
 from time import strftime, time
 
 import numpy as np
@@ -137,13 +138,36 @@ class _Generation:
         self.org_pow, self.dir_prev, self.lineage = org_pow, dir_prev, lineage
         self.n, self.split, self.base = int(n), int(split), int(base)
 
-    def c_struct(self):
+    def c_struct(self, lo=0, hi=None):
+        """The generation - or the ray tile [lo, hi) of it - as the C ABI's lpcl_generation.  A tile
+        is itself a two-segment generation over the same buffers: pointers advanced to logical ray
+        ``lo``, the segment split and base moved accordingly (a tile may straddle the segments)."""
+        hi = self.n if hi is None else hi
+        cap = self.org_pow.shape[0]
+        if lo >= self.split:  # entirely inside the second segment
+            first, split, base = self.base + (lo - self.split), hi - lo, hi - lo
+        else:
+            first, split, base = lo, min(self.split, hi) - lo, self.base - lo
         g = _cabi.Generation()
-        g.d_org_pow = self.org_pow.data_ptr()
-        g.d_dir_prev = self.dir_prev.data_ptr()
-        g.d_lineage = self.lineage.data_ptr() if self.lineage is not None else None
-        g.n, g.seg_split, g.seg_base = self.n, self.split, self.base
-        g.capacity = self.org_pow.shape[0]
+        g.d_org_pow = self.org_pow.data_ptr() + 16 * first
+        g.d_dir_prev = self.dir_prev.data_ptr() + 16 * first
+        g.d_lineage = self.lineage.data_ptr() + 8 * first if self.lineage is not None else None
+        g.n, g.seg_split, g.seg_base = hi - lo, split, base
+        g.capacity = cap - first
+        return g
+
+    def child_struct(self, n_parents, refl_done=0, refr_done=0):
+        """This (still empty) generation as the children argument of one step over a tile of an
+        ``n_parents``-ray parent generation, after earlier tiles produced ``refl_done`` reflected and
+        ``refr_done`` refracted survivors: reflected survivors continue at physical index refl_done,
+        refracted ones at n_parents + refr_done."""
+        g = _cabi.Generation()
+        g.d_org_pow = self.org_pow.data_ptr() + 16 * refl_done
+        g.d_dir_prev = self.dir_prev.data_ptr() + 16 * refl_done
+        g.d_lineage = self.lineage.data_ptr() + 8 * refl_done if self.lineage is not None else None
+        g.n, g.seg_split = 0, 0
+        g.seg_base = n_parents + refr_done - refl_done
+        g.capacity = self.org_pow.shape[0] - refl_done
         return g
 
     def logical(self, t):
@@ -153,6 +177,53 @@ class _Generation:
         if self.split == self.n:
             return t[: self.n]
         return torch.cat((t[: self.split], t[self.base: self.base + (self.n - self.split)]), dim=0)
+
+
+class _HostPool:
+    """Recycles the host memory behind arrays the tracer hands to its caller (flattened vertices,
+    measured (pos, pwr)).  First-touch page faults on newly mapped host memory cost more than the
+    copies themselves (5 ms vs 1 ms for the 18 MB of measured records), so a buffer is handed out
+    again once the caller has dropped EVERY array that refers to it - and only then.
+
+    Ownership is tracked explicitly, not inferred from reference counts: each hand-out wraps the
+    pooled memory in a fresh lease object (a ctypes array over the buffer) and the returned
+    ndarray - and every view, slice or reshape derived from it - keeps that lease alive through
+    NumPy's ``.base`` chain.  ``weakref.finalize`` on the lease marks the buffer free when the last
+    of them is gone."""
+
+    def __init__(self, max_buffers_per_key=4):
+        self._entries = {}
+        self._max = max_buffers_per_key
+
+    class _Entry:
+        __slots__ = ("mem", "busy")
+
+        def __init__(self, mem):
+            self.mem, self.busy = mem, False
+
+        def release(self):
+            self.busy = False
+
+    def array(self, key, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = count * dtype.itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype=dtype)
+        entries = self._entries.setdefault(key, [])
+        entry = next((e for e in entries if not e.busy and e.mem.nbytes >= nbytes), None)
+        if entry is None:
+            entry = self._Entry(np.empty(max(int(nbytes * 1.25), 16384), dtype=np.uint8))
+            if len(entries) >= self._max:  # forget the oldest idle buffer (busy ones stay with their holders)
+                idle = [e for e in entries if not e.busy]
+                if idle:
+                    entries.remove(idle[0])
+            if len(entries) < self._max:
+                entries.append(entry)
+        entry.busy = True
+        lease = (C.c_char * nbytes).from_buffer(entry.mem)
+        weakref.finalize(lease, entry.release)
+        return np.frombuffer(lease, dtype=dtype, count=count).reshape(shape)
 
 
 class TraceResults:
@@ -221,6 +292,10 @@ class CL_Tracer:
                      torch.distributed is initialised).
       shard_input    True: every rank passes the SAME sources and traces its contiguous slice;
                      False: every rank passes its OWN rays (used by bench.py weak scaling).
+      ray_tile_bytes device-memory budget of the per-generation scratch (search results, 12 B per
+                     ray and mesh).  A generation that needs more is traced in RAY TILES that reuse
+                     one scratch buffer, like the reference's <= 50,000-ray partitions (it:218-273);
+                     results are bit-identical.  Default: $LPCL_RAY_TILE_BYTES or 8 GiB.
       profile        record CUDA events around the search and the resolve kernel of every
                      generation -> ``self.kernel_times`` (list of dict(rays, search_ms, resolve_ms)).
     """
@@ -230,7 +305,7 @@ class CL_Tracer:
 
     def __init__(self, platform_name="NVIDIA", device_name="770", debug=False, device=None, keep_results=True,
                  record_hits=False, lineage=None, process_group=None, shard_input=True, verbose=False,
-                 profile=False):
+                 profile=False, ray_tile_bytes=None):
         import torch
 
         self.debug = debug
@@ -250,7 +325,13 @@ class CL_Tracer:
         self.record_hits = record_hits
         self._group = _dist.resolve_group(process_group)
         self.world_size, self.rank = _dist.world(self._group)
+        if self.world_size > 1 and lineage is not None and not lineage:
+            raise ValueError("lineage=False is not possible with world_size > 1: the measured rays of the ranks are "
+                             "merged into the reference order by lineage")
         self._lineage = bool(lineage) if lineage is not None else self.world_size > 1
+        self.ray_tile_bytes = int(ray_tile_bytes if ray_tile_bytes is not None
+                                  else os.environ.get("LPCL_RAY_TILE_BYTES", 8 << 30))
+        self._host_pool = _HostPool()
         self.shard_input = shard_input
         self.profile = profile
         self.kernel_times = []
@@ -409,7 +490,8 @@ class CL_Tracer:
             self._measured_count = 0
             self._measured_per_iter = []
             self.kernel_launches = 0
-            self.stats = dict(rays=[], live=[], power_left=[], candidates=[], measured=[], terminated=[])
+            self.stats = dict(rays=[], live=[], live_local=[], power_left=[], candidates=[], measured=[], terminated=[],
+                              tiles=[])
             counters_dev = torch.zeros(8, dtype=torch.int64, device=self.device)
             if getattr(self, "_counters_host", None) is None:  # pinned once per tracer (cudaHostAlloc is slow)
                 self._counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
@@ -427,10 +509,14 @@ class CL_Tracer:
                 self.kernel_launches += 1
                 gen = _Generation(org_pow, dir_prev, lineage, n, n, n)
 
+            epoch_start = 0  # iteration at which the current lineage numbering started (dist.renumber_lineage)
             for t_iter in range(int(trace_iterations)):
                 n = gen.n if gen is not None else 0
                 if self.verbose:
                     print("ITERATION", t_iter + 1, "with ", n, "rays.")
+                if self._lineage and t_iter - epoch_start >= _dist.PATH_BITS:
+                    self._renumber_lineage(gen)  # a collective with world_size > 1: every rank gets here
+                    epoch_start = t_iter
                 c = dict(n_reflect=0, n_refract=0, n_measured=0, n_terminated=0, live_power=0.0, measured_power=0.0,
                          candidates=0)
                 children = None
@@ -440,36 +526,47 @@ class CL_Tracer:
                     ch_dir = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
                     ch_lin = torch.empty(cap, dtype=torch.int64, device=self.device) if self._lineage else None
                     children = _Generation(ch_org, ch_dir, ch_lin, 0, 0, n)
-                    dest_meas = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+                    tile = self._tile_rays(n)
+                    keep = self.keep_results
+                    dest_meas = torch.empty((n if keep else min(n, tile), 4), dtype=torch.float32, device=self.device)
                     hit = torch.empty((n, 4), dtype=torch.int32, device=self.device) if self.record_hits else None
                     self._reserve_measured(self._measured_count + n)
-                    ws = self._get_workspace(n)
-                    pg, cg = gen.c_struct(), children.c_struct()
-                    counters_dev.zero_()
+                    ws = self._get_workspace(min(n, tile))
+                    ev = []
+                    for lo in range(0, n, tile):
+                        hi = min(lo + tile, n)
+                        pg = gen.c_struct(lo, hi)
+                        cg = children.child_struct(n, c["n_reflect"], c["n_refract"])
+                        dm_ptr = dest_meas.data_ptr() + (16 * lo if keep else 0)
+                        if prof:
+                            ev.append([torch.cuda.Event(enable_timing=True) for _ in range(3)])
+                            ev[-1][0].record(stream)
+                        rc = lib.lpcl_trace_search(self._scene, C.byref(pg), ws.data_ptr(), C.c_float(max_ray_len),
+                                                   counters_dev.data_ptr(), self._stream())
+                        _cabi.check(rc, "lpcl_trace_search")
+                        if prof:
+                            ev[-1][1].record(stream)
+                        rc = lib.lpcl_trace_resolve(
+                            self._scene, C.byref(pg), C.byref(cg), dm_ptr,
+                            hit.data_ptr() + 16 * lo if hit is not None else None, self._measured.data_ptr(),
+                            self._measured_lineage.data_ptr() if self._measured_lineage is not None else None,
+                            self._measured_count + c["n_measured"], self._measured.shape[0], counters_dev.data_ptr(),
+                            ws.data_ptr(), C.c_float(max_ray_len), C.c_float(ior_env), t_iter - epoch_start,
+                            self._stream())
+                        _cabi.check(rc, "lpcl_trace_resolve")
+                        if prof:
+                            ev[-1][2].record(stream)
+                        self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
+                        counters_host.copy_(counters_dev, non_blocking=True)
+                        if lo == 0:
+                            self._ensure_input_power()  # host work hidden behind the kernels just launched
+                        stream.synchronize()
+                        sc = _cabi.StepCounters.from_buffer_copy(counters_host.numpy().tobytes())
+                        for k, _ in _cabi.StepCounters._fields_:
+                            if k != "reserved":
+                                c[k] += getattr(sc, k)
                     if prof:
-                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-                        ev[0].record(stream)
-                    rc = lib.lpcl_trace_search(self._scene, C.byref(pg), ws.data_ptr(), C.c_float(max_ray_len),
-                                               counters_dev.data_ptr(), self._stream())
-                    _cabi.check(rc, "lpcl_trace_search")
-                    if prof:
-                        ev[1].record(stream)
-                    rc = lib.lpcl_trace_resolve(
-                        self._scene, C.byref(pg), C.byref(cg), dest_meas.data_ptr(),
-                        hit.data_ptr() if hit is not None else None, self._measured.data_ptr(),
-                        self._measured_lineage.data_ptr() if self._measured_lineage is not None else None,
-                        self._measured_count, self._measured.shape[0], counters_dev.data_ptr(), ws.data_ptr(),
-                        C.c_float(max_ray_len), C.c_float(ior_env), t_iter, self._stream())
-                    _cabi.check(rc, "lpcl_trace_resolve")
-                    if prof:
-                        ev[2].record(stream)
                         events.append((n, ev))
-                    self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
-                    counters_host.copy_(counters_dev, non_blocking=True)
-                    self._ensure_input_power()  # host work hidden behind the kernels just launched
-                    stream.synchronize()
-                    sc = _cabi.StepCounters.from_buffer_copy(counters_host.numpy().tobytes())
-                    c = {k: getattr(sc, k) for k, _ in _cabi.StepCounters._fields_}
                     children.n = c["n_reflect"] + c["n_refract"]
                     children.split = c["n_reflect"]
                     if self.keep_results:
@@ -491,11 +588,13 @@ class CL_Tracer:
 
                 # it:372-391, evaluated over ALL ranks
                 input_power = self._ensure_input_power()
-                live, power_left = c["n_reflect"] + c["n_refract"], c["live_power"]
+                live_local = c["n_reflect"] + c["n_refract"]
+                live, power_left = live_local, c["live_power"]
                 if self.world_size > 1:
                     live, power_left = _dist.all_reduce_pair(live, power_left, self._group, self.device)
-                for k, v in (("rays", n), ("live", live), ("power_left", power_left), ("candidates", c["candidates"]),
-                             ("measured", c["n_measured"]), ("terminated", c["n_terminated"])):
+                for k, v in (("rays", n), ("live", live), ("live_local", live_local), ("power_left", power_left),
+                             ("candidates", c["candidates"]), ("measured", c["n_measured"]),
+                             ("terminated", c["n_terminated"]), ("tiles", -(-n // self._tile_rays(n)) if n else 0)):
                     self.stats[k].append(v)
                 gen = children if (children is not None and children.n > 0) else None
                 if self.verbose:
@@ -506,8 +605,9 @@ class CL_Tracer:
                     break
             if prof:
                 stream.synchronize()
-                self.kernel_times = [dict(rays=n_, search_ms=e[0].elapsed_time(e[1]), resolve_ms=e[1].elapsed_time(e[2]))
-                                     for n_, e in events]
+                self.kernel_times = [dict(rays=n_, search_ms=sum(e[0].elapsed_time(e[1]) for e in ev_),
+                                          resolve_ms=sum(e[1].elapsed_time(e[2]) for e in ev_), tiles=len(ev_))
+                                     for n_, ev_ in events]
         self.timings["run_s"] = time() - t_start
         return self.results
 
@@ -525,6 +625,23 @@ class CL_Tracer:
                 lin[: self._measured_count] = self._measured_lineage[: self._measured_count]
         self._measured, self._measured_lineage = buf, lin
 
+    def _tile_rays(self, n):
+        """Rays per tile of a generation of n rays: as many as the scratch budget allows (12 B per
+        ray and mesh + the per-tile end points), in multiples of 4096, at least 65,536."""
+        per_ray = 12 * int(self.mesh_count) + 16 + 1
+        tile = max(65536, (self.ray_tile_bytes // per_ray) // 4096 * 4096)
+        return n if n <= tile else tile
+
+    def _renumber_lineage(self, gen):
+        """Start a new lineage epoch (the 31 branch bits of the 64-bit id are used up): every live
+        ray's id becomes its rank in the generation's global reference order."""
+        torch = self._torch
+        keys = gen.logical(gen.lineage) if gen is not None else torch.zeros(0, dtype=torch.int64, device=self.device)
+        new = _dist.renumber_lineage(keys, self._group, self.device)
+        if gen is not None:
+            gen.lineage[: gen.split] = new[: gen.split]
+            gen.lineage[gen.base: gen.base + (gen.n - gen.split)] = new[gen.split:]
+
     # ---------------------------------------------------------------------------------- results
     def get_measured_rays(self, gather=True):
         """it:395-411: ``(pos (K,4) f32, pwr (K,) f32)`` of every ray that ended on a measure
@@ -536,8 +653,9 @@ class CL_Tracer:
         pos_pwr = self.measured_device()
         per_iter = list(self._measured_per_iter)
         if self.world_size > 1 and gather:
-            pos_pwr = _dist.gather_measured(pos_pwr, self._measured_lineage[: self._measured_count], per_iter,
-                                            self._group, self.device)
+            lin = (self._measured_lineage[: self._measured_count] if self._measured_lineage is not None
+                   else self._torch.zeros(0, dtype=self._torch.int64, device=self.device))  # a rank that never had rays
+            pos_pwr = _dist.gather_measured(pos_pwr, lin, per_iter, self._group, self.device)
         if pos_pwr.is_cuda:  # split (x, y, z, power) on the GPU: two device->host copies, no host passes
             pwr_dev = pos_pwr[:, 3].contiguous()
             pos_dev = pos_pwr.clone()
@@ -555,23 +673,9 @@ class CL_Tracer:
         return (pos, pwr)
 
     def _host_array(self, name, rows, cols, dtype):
-        """A ``(rows, cols)`` (or ``(rows,)`` when cols == 0) host array whose memory is recycled.
-        First-touch page faults on newly mapped host memory cost more than the copies themselves (5 ms
-        vs 1 ms for the 18 MB of measured records), so the backing buffer of an array nobody holds any
-        more is handed out again - and only then: a buffer is reused when nothing but this pool
-        references it, so arrays already returned to the caller are never overwritten."""
-        import sys
-
-        pool = self.__dict__.setdefault("_host_pool", {}).setdefault((name, cols, np.dtype(dtype).str), [])
-        for base in pool:
-            if len(base) >= rows and sys.getrefcount(base) <= 3:  # the pool list, the loop variable, the argument
-                return base[:rows]
-        cap = max(int(rows * 1.25), 1024)
-        base = np.empty((cap, cols) if cols else cap, dtype=dtype)
-        if len(pool) >= 4:
-            pool.pop(0)
-        pool.append(base)
-        return base[:rows]
+        """A ``(rows, cols)`` (or ``(rows,)`` when cols == 0) host array from the recycling pool
+        (``_HostPool``): its memory is reused only after the caller dropped every array derived from it."""
+        return self._host_pool.array((name, cols, np.dtype(dtype).str), (rows, cols) if cols else (rows,), dtype)
 
     def _host_result_arrays(self, k):
         """``(pos (k,4), pwr (k,))`` float32 arrays for get_measured_rays, from the recycling pool."""

@@ -33,24 +33,23 @@ def _Rz(a):
 
 
 def _pinned(a):
-    """The same float32 values in page-locked host memory when a CUDA device is present, so that the
-    tracer's host->device copy of the rays is a direct DMA (pageable memory is staged at ~1/4 of the
-    rate).  A no-op without CUDA or with LPCL_PIN_SOURCES=0; the array keeps its owner alive."""
+    """Opt-in (``LPCL_PIN_SOURCES=1``): the same float32 values in page-locked host memory, so that
+    the tracer's host->device copy of the rays is a direct DMA (pageable memory is staged at ~1/4 of
+    the rate; 4.1 -> 0.9 ms for 1M rays).  By default this class is plain NumPy like the reference's
+    and touches neither torch nor CUDA: no context is created before the tracer has picked its
+    device, fork-based multiprocessing keeps working, nothing is page-locked behind the caller's back."""
     import os
 
-    if os.environ.get("LPCL_PIN_SOURCES", "1") == "0" or a is None:
+    if a is None or os.environ.get("LPCL_PIN_SOURCES", "0") != "1":
         return a
-    try:
-        import torch
+    import torch
 
-        if not torch.cuda.is_available():
-            return a
-        a = np.ascontiguousarray(a)
-        if a.dtype != np.float32 or a.size == 0:
-            return a
-        return torch.from_numpy(a).pin_memory().numpy()
-    except Exception:  # no torch / no driver: plain NumPy arrays, as the reference has them
+    if not torch.cuda.is_available():
         return a
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.float32 or a.size == 0:
+        return a
+    return torch.from_numpy(a).pin_memory().numpy()
 
 
 class light_source:

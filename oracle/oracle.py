@@ -232,7 +232,7 @@ def ray_triangle(O, D, V0, V1, V2, backend="port"):
 
 # ----------------------------------------------------------------------------- host loop
 def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.99, max_ray_len=np.float32(1e3),
-          ior_env=np.float32(1.0), backend="port", keep_debug=True, power_sum="reference"):
+          ior_env=np.float32(1.0), backend="port", keep_debug=True, power_sum="reference", lineage0=None):
     """Restatement of CL_Tracer.iterative_tracer (it:77-393).
 
     Returns a dict with
@@ -245,6 +245,10 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
       input_power, tri_count, scene
     ``power_sum``: "reference" = sorted sequential float32 sum (it:372); "f64" = float64 sum, the
     rule the GPU path uses.  The break test itself is evaluated in float64 for both.
+    ``lineage0``: optional int64 id per source ray; the result then carries ``lineage`` (one int64
+    array per iteration, aligned with ``results``): a child keeps its parent's id, the refracted
+    child of iteration k additionally gets bit 32 + k - the id the CUDA path carries, which lets a
+    test match the rays of a sub-sampled oracle run with those of a full-size GPU run.
     """
     max_ray_len = np.float32(max_ray_len)
     ior_env = np.float32(ior_env)
@@ -255,8 +259,9 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
     prev_mesh = np.zeros(n, dtype=np.int32) - 2
     scene = Scene(meshes)
 
-    results, debug, live, power_left = [], [], [], []
-    for _ in range(int(trace_iterations)):
+    results, debug, live, power_left, lineages = [], [], [], [], []
+    lin = None if lineage0 is None else np.asarray(lineage0, dtype=np.int64).copy()
+    for k_iter in range(int(trace_iterations)):
         n = len(origin)
         pw = np.ascontiguousarray(rays_pow.reshape(-1), dtype=np.float32)  # kernels see a flat float buffer
         ms = np.ascontiguousarray(rays_meas, dtype=np.int32)
@@ -265,6 +270,8 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
         ch = reflect_refract(scene, origin, pp["dest"], direc, pw, ms, pp["n1"], pp["n2"], pp["hit_mesh"],
                              pp["hit_tri"], ior_env, max_ray_len, backend)
         results.append((origin, pp["dest"], pw.reshape(rays_pow.shape), ms))
+        if lin is not None:
+            lineages.append(lin)
         if keep_debug:
             d = dict(pp)
             d.update(near_t=near_t, hits=hits, near_tri=near_tri, dir=direc, prev_mesh=prev_mesh)
@@ -278,6 +285,9 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
         rays_pow = np.ascontiguousarray(np.concatenate((ch["refl_power"], ch["refr_power"]), axis=0)[idx])
         rays_meas = np.ascontiguousarray(child_meas[idx].astype(np.int32))
         prev_mesh = np.ascontiguousarray(np.concatenate((pp["hit_mesh"], pp["hit_mesh"]), axis=0)[idx])
+        if lin is not None:
+            branch = (np.int64(1) << np.int64(32 + k_iter)) if k_iter < 31 else np.int64(0)
+            lin = np.concatenate((lin, lin | branch), axis=0)[idx]
 
         if power_sum == "reference":
             p_scene = float(seq_sum_sorted_f32(rays_pow))
@@ -290,7 +300,7 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
         if len(origin) == 0:
             break  # it:389-391
     return dict(results=results, debug=debug, live=live, power_left=power_left, input_power=input_power,
-                tri_count=scene.tri_count, scene=scene)
+                tri_count=scene.tri_count, scene=scene, lineage=lineages)
 
 
 def measured_rays(results):

@@ -162,26 +162,59 @@ def test_flatten_fast_path_equals_tribuf_path():
 
 def test_measured_result_buffers_are_reused_only_when_dropped():
     """get_measured_rays hands out arrays backed by a small pool (first-touch page faults of fresh host
-    memory cost more than the copy): a backing buffer may be reused only when the caller holds no view
-    of it any more - results already handed out must never be overwritten."""
+    memory cost more than the copy): a backing buffer may be reused only when the caller holds no array
+    derived from it any more - results already handed out must never be overwritten.  Ownership is
+    tracked by an explicit lease per hand-out (not by reference counts)."""
+    import gc
+
+    from lightpycl_b200.iterative_tracer import _HostPool
+
+    pool = _HostPool()
+    key = ("pos", 4, np.dtype(np.float32).str)
+    a = pool.array(key, (1000, 4), np.float32)
+    a[:] = 1.0
+    a2 = pool.array(key, (900, 4), np.float32)  # a still referenced: different memory
+    assert not np.shares_memory(a, a2)
+    addr = a.ctypes.data
+    del a
+    gc.collect()
+    a3 = pool.array(key, (800, 4), np.float32)  # first array dropped: its memory is reused
+    assert a3.ctypes.data == addr and len(pool._entries[key]) == 2
+    # every kind of derived array protects the buffer: a slice, a column view, a reshape, a dtype view
+    for derive in (lambda x: x[:10], lambda x: x[:, :3], lambda x: x.reshape(-1), lambda x: x.view(np.uint32)):
+        held = pool.array(key, (700, 4), np.float32)
+        held[:] = 7.0
+        keep = derive(held)
+        del held
+        gc.collect()
+        others = [pool.array(key, (700, 4), np.float32) for _ in range(3)]
+        for o in others:
+            o[:] = -1.0
+            assert not np.shares_memory(keep, o)
+        assert np.all(keep.view(np.float32) == 7.0)
+        del keep, others, o
+        gc.collect()
+    big = pool.array(key, (5000, 4), np.float32)  # larger than any pooled buffer: a new one
+    assert big.shape == (5000, 4) and big.dtype == np.float32
+    assert pool.array(key, (0, 4), np.float32).shape == (0, 4)
+
+
+def test_a_held_result_survives_later_calls():
+    """The user-level version of the above: hold the first (pos, pwr) across more hand-outs."""
     from lightpycl_b200.iterative_tracer import CL_Tracer
 
-    class Holder:  # the pool only needs an attribute dict
+    class Holder:  # _host_result_arrays only needs the pool
         _host_array = CL_Tracer._host_array
 
+    from lightpycl_b200.iterative_tracer import _HostPool
+
     t = Holder()
-    take = CL_Tracer._host_result_arrays
-    a, b = take(t, 1000)
-    a[:] = 1.0
-    a2, b2 = take(t, 900)                       # a, b still referenced: different memory
-    assert not np.shares_memory(a, a2) and not np.shares_memory(b, b2)
-    del a, b
-    a3, b3 = take(t, 800)                       # first set dropped: reused
-    pos_pool = t._host_pool[("pos", 4, np.dtype(np.float32).str)]
-    assert a3.base is pos_pool[0] and len(pos_pool) == 2
-    keep = a3[:10]                              # a view of a view still protects the buffer
-    del a3, b3
-    a4, _ = take(t, 700)
-    assert not np.shares_memory(keep, a4)
-    big, _ = take(t, 5000)                      # larger than any pooled buffer: a new one
-    assert big.shape == (5000, 4) and big.dtype == np.float32
+    t._host_pool = _HostPool()
+    pos, pwr = CL_Tracer._host_result_arrays(t, 1000)
+    pos[:], pwr[:] = 3.0, 4.0
+    xyz = pos[:, :3]
+    del pos
+    for _ in range(6):
+        p2, w2 = CL_Tracer._host_result_arrays(t, 1000)
+        p2[:], w2[:] = 0.0, 0.0
+    assert np.all(xyz == 3.0) and np.all(pwr == 4.0)
