@@ -204,6 +204,25 @@ def dissipative_cube(ray_count=10_000, trace_iterations=16, ior=1.0, dissipation
     return [src], [dome, block], params
 
 
+def glass_cube_cavity(ray_count=1000, trace_iterations=40):
+    """A source INSIDE a glass cube (IOR 1.5, edge 10) inside a measure sphere (r = 100): at every bounce
+    the internally reflected ray stays in the cube (totally, beyond 41.8 degrees) and the refracted one
+    leaves and is measured on the sphere one iteration later.  The ray count stays bounded while the
+    trace runs to any depth with measured rays in every generation - the deep-trace case behind the
+    reference's default of 100 iterations (it:77) and the lineage epochs of dist.renumber_lineage.
+    ``trace_until_dissipated = 1.0``: the power test never fires."""
+    src = _source(0, center=np.array([0.5, -0.25, 0.125, 0], dtype=np.float32), direction=(0, 0, 1), directivity=_cosine,
+                  power=1000.0, ray_count=ray_count)
+    oe = goe.optical_elements()
+    shell = oe.sphere(center=[0, 0, 0, 0], radius=100.0)
+    shell.setMaterial(mat_type="measure")
+    cube = oe.cube(center=(0, 0, 0, 0), size=[10, 10, 10, 0])
+    cube.setMaterial(mat_type="refractive", IOR=1.5)
+    params = dict(trace_iterations=trace_iterations, trace_until_dissipated=1.0, max_ray_len=np.float32(1.0e3),
+                  ior_env=np.float32(1.0))
+    return [src], [shell, cube], params
+
+
 def lenslet_array_per_mesh(ray_count=1_000_000, **kw):
     """C5' - the lenslet array with every lenslet its own mesh (mesh_count = 66): stresses the
     per-(ray, mesh) search scratch and the generic (M > 8) media-resolution path."""
@@ -218,4 +237,5 @@ CONFIGS = {
     "c4_human_eye": human_eye,
     "c5_lenslet_array": lenslet_array,
     "dissipative_cube": dissipative_cube,
+    "glass_cube_cavity": glass_cube_cavity,
 }

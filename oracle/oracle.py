@@ -248,7 +248,9 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
     ``lineage0``: optional int64 id per source ray; the result then carries ``lineage`` (one int64
     array per iteration, aligned with ``results``): a child keeps its parent's id, the refracted
     child of iteration k additionally gets bit 32 + k - the id the CUDA path carries, which lets a
-    test match the rays of a sub-sampled oracle run with those of a full-size GPU run.
+    test match the rays of a sub-sampled oracle run with those of a full-size GPU run.  Every 31
+    iterations (the branch bits of a 64-bit id) a new epoch starts: ids become 0..n-1 in generation
+    order and the branch bits start over, as lightpycl_b200.dist.renumber_lineage does.
     """
     max_ray_len = np.float32(max_ray_len)
     ior_env = np.float32(ior_env)
@@ -261,7 +263,10 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
 
     results, debug, live, power_left, lineages = [], [], [], [], []
     lin = None if lineage0 is None else np.asarray(lineage0, dtype=np.int64).copy()
+    epoch_start = 0
     for k_iter in range(int(trace_iterations)):
+        if lin is not None and k_iter - epoch_start >= 31:
+            lin, epoch_start = np.arange(len(lin), dtype=np.int64), k_iter
         n = len(origin)
         pw = np.ascontiguousarray(rays_pow.reshape(-1), dtype=np.float32)  # kernels see a flat float buffer
         ms = np.ascontiguousarray(rays_meas, dtype=np.int32)
@@ -286,7 +291,7 @@ def trace(light_source, meshes, trace_iterations=100, trace_until_dissipated=0.9
         rays_meas = np.ascontiguousarray(child_meas[idx].astype(np.int32))
         prev_mesh = np.ascontiguousarray(np.concatenate((pp["hit_mesh"], pp["hit_mesh"]), axis=0)[idx])
         if lin is not None:
-            branch = (np.int64(1) << np.int64(32 + k_iter)) if k_iter < 31 else np.int64(0)
+            branch = np.int64(1) << np.int64(32 + k_iter - epoch_start)
             lin = np.concatenate((lin, lin | branch), axis=0)[idx]
 
         if power_sum == "reference":

@@ -45,8 +45,12 @@ def _sharded_oracle_trace(rank, world, port, scene_name, kw, out_dir):
     scene = oracle.Scene(meshes)
     mrl, env = np.float32(params["max_ray_len"]), np.float32(params["ior_env"])
     recs, lins, per_iter, lives = [], [], [], []
+    epoch_start = 0
     for it in range(params["trace_iterations"]):
         n = len(origin)
+        if it - epoch_start >= dist.PATH_BITS:  # the branch bits are used up: new lineage epoch (a collective)
+            lineage = dist.renumber_lineage(torch.from_numpy(lineage), group, "cpu").numpy()
+            epoch_start = it
         meas = np.zeros(n, np.int32)
         if n:
             nt, h, ni = oracle.intersect(scene, origin, direc, mrl)
@@ -58,8 +62,8 @@ def _sharded_oracle_trace(rank, world, port, scene_name, kw, out_dir):
             lins.append(lineage[m])
             per_iter.append(int(m.sum()))
             keep = np.concatenate((ch["refl_meas"], ch["refr_meas"])) == 0
-            # lineage rule of the step kernel: refracted children set bit (32 + iteration)
-            lineage = np.concatenate((lineage, lineage | (np.int64(1) << (32 + it))))[keep]
+            # lineage rule of the step kernel: refracted children set bit (32 + iteration within the epoch)
+            lineage = np.concatenate((lineage, lineage | (np.int64(1) << (32 + it - epoch_start))))[keep]
             origin = np.ascontiguousarray(np.concatenate((ch["refl_origin"], ch["refr_origin"]))[keep])
             direc = np.ascontiguousarray(np.concatenate((ch["refl_dir"], ch["refr_dir"]))[keep])
             pw = np.ascontiguousarray(np.concatenate((ch["refl_power"], ch["refr_power"]))[keep])
@@ -81,7 +85,11 @@ def _sharded_oracle_trace(rank, world, port, scene_name, kw, out_dir):
 
 @pytest.mark.parametrize("scene_name,kw", [("c2_directivity_lens", dict(ray_count=301)),
                                            ("c1_nested_cubes", dict(ray_count=400)),
-                                           ("c4_human_eye", dict(ray_count=40, sources=2, trace_iterations=5))])
+                                           ("c4_human_eye", dict(ray_count=40, sources=2, trace_iterations=5)),
+                                           # 40 generations: past the 31 branch bits of a lineage id (renumbering)
+                                           ("glass_cube_cavity", dict(ray_count=61, trace_iterations=40)),
+                                           # fewer rays than ranks: rank 0 traces nothing and still gathers
+                                           ("glass_cube_cavity", dict(ray_count=1, trace_iterations=6))])
 def test_two_rank_sharded_trace_equals_single_process(tmp_path, scene_name, kw):
     sys.path.insert(0, ROOT)
     from lightpycl_b200 import scenes
@@ -101,6 +109,14 @@ def test_two_rank_sharded_trace_equals_single_process(tmp_path, scene_name, kw):
         assert np.array_equal(z["merged"][:, :3].view(np.uint32), np.ascontiguousarray(pos[:, :3]).view(np.uint32))
         assert np.array_equal(z["merged"][:, 3].copy().view(np.uint32),
                               np.ascontiguousarray(np.asarray(pwr).reshape(-1)).view(np.uint32))
+
+
+def test_renumber_lineage_single_process_is_dense_order():
+    from lightpycl_b200 import dist
+
+    keys = torch.tensor([3, 7 | (1 << 40), 9 | (1 << 62)], dtype=torch.int64)
+    assert dist.renumber_lineage(keys, None, "cpu").tolist() == [0, 1, 2]
+    assert dist.renumber_lineage(keys[:0], None, "cpu").tolist() == []
 
 
 def test_merge_measured_orders_by_iteration_then_lineage():

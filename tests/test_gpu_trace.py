@@ -241,3 +241,70 @@ def test_empty_source():
     assert o.shape == (0, 4) and d.shape == (0, 4) and p.shape == (0,) and m.shape == (0,)
     pos, pwr = tr.get_measured_rays()
     assert pos.shape == (0, 4) and np.asarray(pwr).size == 0
+
+
+def test_ray_tiles_give_bit_identical_results(monkeypatch):
+    """HBM-bounded ray tiling (the reference's <= 50,000-ray partitions, it:218-273): with a tiny
+    scratch budget every generation of C2 at 100k rays is traced in several ray tiles that reuse one
+    scratch buffer; `results`, hit records and measured rays must equal the untiled run bit for bit."""
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=100_000)
+    whole = _trace_gpu(ls, meshes, params, lineage=True)
+    assert max(whole.stats["tiles"]) == 1
+    tiled = _trace_gpu(ls, meshes, params, lineage=True, ray_tile_bytes=1)  # -> the 65,536-ray minimum tile
+    assert min(t for t, n in zip(tiled.stats["tiles"], tiled.stats["rays"]) if n > 65536) >= 2
+    assert tiled.results.ray_counts == whole.results.ray_counts and tiled.stats["live"] == whole.stats["live"]
+    util.assert_results_equal(list(tiled.results), list(whole.results), "tiled vs whole")
+    for a, b in zip(tiled.hit_records, whole.hit_records):
+        assert bool((a == b).all())
+    for (ga, _d, _p), (gb, _d2, _p2) in zip(tiled.results._dev, whole.results._dev):
+        assert bool((ga.logical(ga.lineage) == gb.logical(gb.lineage)).all())
+        import torch
+
+        assert bool((ga.logical(ga.dir_prev).view(torch.int32) == gb.logical(gb.dir_prev).view(torch.int32)).all())
+    pa, pb = tiled.get_measured_rays(), whole.get_measured_rays()
+    assert np.array_equal(util.bits(pa[0]), util.bits(pb[0])) and np.array_equal(util.bits(np.asarray(pa[1])),
+                                                                                  util.bits(np.asarray(pb[1])))
+    # the budget can also come from the environment, and without retained results the end points are per-tile scratch
+    monkeypatch.setenv("LPCL_RAY_TILE_BYTES", "4000000")
+    lean = _trace_gpu(ls, meshes, params, keep_results=False)
+    assert max(lean.stats["tiles"]) >= 2
+    pc = lean.get_measured_rays()
+    assert np.array_equal(util.bits(pc[0]), util.bits(pb[0])) and np.array_equal(util.bits(np.asarray(pc[1])),
+                                                                                  util.bits(np.asarray(pb[1])))
+
+
+def test_deep_trace_lineage_epochs():
+    """40 generations (the reference allows 100 by default, it:77): past the 31 branch bits of a 64-bit
+    lineage id the tracer starts a new lineage epoch; results stay bit-identical to the oracle and
+    every generation's ids stay strictly increasing (= the reference order) and equal the oracle's."""
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.glass_cube_cavity(ray_count=500, trace_iterations=40)
+    tr, ref = _check("cavity", ls, meshes, params, lineage=True)
+    assert len(tr.results) == 40 and min(tr.stats["measured"][1:]) > 0
+    want = oracle.trace(ls, meshes, power_sum="f64", lineage0=np.arange(500), **params)["lineage"]
+    for k, (gen, _dm, _ps) in enumerate(tr.results._dev):
+        lin = gen.logical(gen.lineage).cpu().numpy()
+        assert np.all(np.diff(lin) > 0), k
+        assert np.array_equal(lin, want[k]), k
+
+
+def test_held_results_survive_later_traces():
+    """arrays returned by get_measured_rays / tr.geometry must never be overwritten by a later
+    call that recycles host buffers."""
+    from lightpycl_b200 import scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=5000)
+    tr = _trace_gpu(ls, meshes, params)
+    pos, pwr = tr.get_measured_rays()
+    geo0 = tr.geometry[0]
+    xyz, pw_copy, geo_copy = pos[:, :3], np.array(pwr, copy=True), np.array(geo0, copy=True)
+    xyz_copy = np.array(xyz, copy=True)
+    del pos
+    ls2, meshes2, params2 = scenes.parabolic_mirror(ray_count=5000, profile_pts=40, ang_pts=17)
+    for _ in range(5):
+        tr.iterative_tracer(ls2, meshes2, **params2)
+        tr.get_measured_rays()
+    assert np.array_equal(xyz, xyz_copy) and np.array_equal(pwr, pw_copy) and np.array_equal(geo0, geo_copy)
