@@ -15,6 +15,10 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
+# the checker: the reference kernels themselves (oracle/_ref, compiled from the reference .cl) where present,
+# else the C restatement pinned to them on the CPU (tests/test_oracle_pinning.py)
+BACKEND = "reference" if oracle.available("reference") else "port"
+
 
 class GpuSeams:
     def __init__(self, scene):
@@ -113,7 +117,7 @@ NAMES = ["c1_cubes_10", "c1_cubes_300", "mini_lens", "mini_mirror", "mini_lossy"
 @pytest.mark.parametrize("name", NAMES)
 def test_three_seams_match_oracle(name):
     ls, meshes, params = _get(name)
-    ref = oracle.trace(ls, meshes, backend="port", **params)
+    ref = oracle.trace(ls, meshes, backend=BACKEND, **params)
     g = GpuSeams(ref["scene"])
     try:
         mrl = np.float32(params["max_ray_len"])
@@ -139,7 +143,8 @@ def test_three_seams_match_oracle(name):
                 p_in = p_next
             m_in = np.zeros(len(origin), np.int32)
             want = oracle.reflect_refract(ref["scene"], origin, dest, direc, p_in.copy(), m_in.copy(), dbg["n1"],
-                                          dbg["n2"], dbg["hit_mesh"], dbg["hit_tri"], np.float32(params["ior_env"]), mrl)
+                                          dbg["n2"], dbg["hit_mesh"], dbg["hit_tri"], np.float32(params["ior_env"]), mrl,
+                                          BACKEND)
             got = g.reflect_refract(origin, dest, direc, p_in.copy(), m_in.copy(), dbg["n1"], dbg["n2"],
                                     dbg["hit_mesh"], dbg["hit_tri"], np.float32(params["ior_env"]))
             for key in ("refl_power", "refr_power", "refl_meas", "refr_meas"):
@@ -184,7 +189,7 @@ def test_search_variants_agree(impl, R, chunks):
     ls, meshes, params = scenes.directivity_lens(ray_count=5000)
     sc = oracle.Scene(meshes)
     origin, direc, _, _ = oracle.flatten_sources(ls)
-    want = oracle.intersect(sc, origin, direc, params["max_ray_len"], "port")
+    want = oracle.intersect(sc, origin, direc, params["max_ray_len"], BACKEND)
     g = GpuSeams(sc)
     _set_search(impl, R, chunks)
     try:
@@ -270,7 +275,7 @@ def test_resolve_and_scatter_seams_on_random_inputs(seed):
     near_tri[near_t >= max_ray_len] = -1
     prev = rng.randint(-2, M, n).astype(np.int32)
 
-    want = oracle.postproc(sc, origin, direc, prev, near_t, hits, near_tri, max_ray_len, "port")
+    want = oracle.postproc(sc, origin, direc, prev, near_t, hits, near_tri, max_ray_len, BACKEND)
     g = GpuSeams(sc)
     try:
         got = g.postproc(origin, direc, prev, near_t, hits, near_tri, max_ray_len)
@@ -285,11 +290,11 @@ def test_resolve_and_scatter_seams_on_random_inputs(seed):
         measured = rng.choice([0, 0, 0, 0, 1, -1], size=n).astype(np.int32)
         args = (origin, want["dest"], direc)
         w = oracle.reflect_refract(sc, *args, power.copy(), measured.copy(), want["n1"], want["n2"], want["hit_mesh"],
-                                   want["hit_tri"], np.float32(1.0), max_ray_len, "port")
+                                   want["hit_tri"], np.float32(1.0), max_ray_len, BACKEND)
         # the oracle call updates its power/measured arguments in place: redo with kept copies
         p_ref, m_ref = power.copy(), measured.copy()
         w = oracle.reflect_refract(sc, *args, p_ref, m_ref, want["n1"], want["n2"], want["hit_mesh"], want["hit_tri"],
-                                   np.float32(1.0), max_ray_len, "port")
+                                   np.float32(1.0), max_ray_len, BACKEND)
         got = g.reflect_refract(origin, want["dest"], direc, power.copy(), measured.copy(), want["n1"], want["n2"],
                                 want["hit_mesh"], want["hit_tri"], np.float32(1.0))
         ok = np.isfinite(w["refl_dir"]).all(axis=1) & np.isfinite(w["refr_dir"]).all(axis=1) & \
@@ -371,7 +376,7 @@ def test_search_on_adversarial_triangle_soup(seed, scale):
     direc = pad(d3)
     max_ray_len = np.float32(60.0 * scale)
 
-    want = oracle.intersect(sc, origin, direc, max_ray_len, "port")
+    want = oracle.intersect(sc, origin, direc, max_ray_len, BACKEND)
     g = GpuSeams(sc)
     try:
         for impl, R, chunks in (("simt", 0, 0), ("simt", 4, 5), ("simt", 1, 3), ("tc", 0, 0), ("tc", 1, 3), ("tc", 4, 5)):
@@ -420,7 +425,7 @@ def test_search_with_thousands_of_coincident_triangles(impl):
     direc = pad(d3 / np.linalg.norm(d3, axis=1, keepdims=True))
     max_ray_len = np.float32(100.0)
 
-    want = oracle.intersect(sc, origin, direc, max_ray_len, "port")
+    want = oracle.intersect(sc, origin, direc, max_ray_len, BACKEND)
     assert (want[1][:, 0] == copies).all() and (want[1][:, 1] == 1).all()     # every ray: 3,000 + 1 crossings
     assert (want[2][:, 0] < 2).all()                                             # ties: the first copy wins
     g = GpuSeams(sc)

@@ -95,3 +95,26 @@ def test_power_sum_rules_agree_on_fixtures():
             continue  # negative IOR: child powers of +-1e5 cancel, the two sums differ in the 3rd digit
         for x, y in zip(a["power_left"], b["power_left"]):
             assert abs(x - y) <= 1e-5 * max(abs(x), 1e-30) + 1e-9
+
+
+def test_c1_both_power_sum_rules_give_the_same_generations():
+    """the GPU path ends the trace on a float64 sum of the surviving power, the
+    reference on a sorted sequential float32 sum (it:372).  On C1 (negative IOR: child powers of
+    +-1e5 cancel, so the two sums differ in the third digit) the BREAK DECISIONS must still agree:
+    identical `live` lists, at 300 and at 1,000 rays, with the reference kernels where present.
+    Tolerance statement: the rule is a threshold test on
+    power_left < 0.01 * input_power; the two sums differ by <= 1e-2 relative on C1 and <= 1e-5
+    elsewhere, so a decision could only flip for a generation whose surviving power lies within that
+    band of the threshold - none of the configurations has one (closest approach asserted below)."""
+    from lightpycl_b200 import scenes
+
+    backend = "reference" if oracle.available("reference") else "port"
+    for n in (300, 1000):
+        ls, meshes, params = scenes.nested_cubes(ray_count=n)
+        a = oracle.trace(ls, meshes, backend=backend, power_sum="reference", **params)
+        b = oracle.trace(ls, meshes, backend=backend, power_sum="f64", **params)
+        assert a["live"] == b["live"] and len(a["results"]) == len(b["results"])
+        thr = 0.01 * float(np.asarray(a["input_power"]).reshape(-1)[0])
+        for x, y in zip(a["power_left"], b["power_left"]):
+            assert (x < thr) == (y < thr)
+            assert min(abs(x - thr), abs(y - thr)) > 4.0 * abs(x - y)  # no generation near the threshold
