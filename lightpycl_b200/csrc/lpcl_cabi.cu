@@ -554,6 +554,15 @@ extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *paren
                               stream_);
 }
 
+#ifdef LPCL_TC_TRACE
+extern "C" int lpcl_debug_read_trace(void *h_dst, int64_t bytes) // development build only (see lpcl_search_tc.cuh)
+{
+    cudaDeviceSynchronize();
+    CUDA_TRY(cudaMemcpyFromSymbol(h_dst, g_tc_trace, bytes < (int64_t)sizeof(g_tc_trace) ? (size_t)bytes : sizeof(g_tc_trace)));
+    return 0;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------ post-processing
 #include "lpcl_project.cuh"
 

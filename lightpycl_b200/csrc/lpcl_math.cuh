@@ -218,22 +218,37 @@ LPCL_HD bool filter_candidate(const FilterRec &q, float dx, float dy, float dz, 
 // The same filter evaluated by the tensor cores (lpcl_search_tc.cuh).
 //
 // DEN, uN and vN are linear in the ray's six numbers (M, D), so a tile of rays x a tile of
-// triangles is a GEMM with K = 6: D[ray][3 t + {0,1,2}] = (M, D)_ray . row_{t,{DEN,uN,vN}}.  The
+// triangles is a GEMM with K = 6: D[ray][3 t + {0,1,2}] = (M, D)_ray . row_{t,{0,1,2}}.  The
 // tensor cores multiply TF32 (11-bit significands), so every fp32 operand x is split into
 // x = hi + lo (+ <= 2^-22 |x|), hi = tf32(x), lo = tf32(x - hi), and the four partial products
 // hi.hi + hi.lo + lo.hi + lo.lo are laid along K (4 x 6 = 24 = three kind::tf32 MMAs of K = 8).
+//
+// The three rows per triangle are DEN, aU = 2 uN - DEN and aV = 2 vN - DEN (still linear in the
+// ray), because  uN (DEN - uN) = (DEN^2 - aU^2) / 4 :  the two product tests become
+//   DEN^2 + m - aU^2 >= 0   and   DEN^2 + m - aV^2 >= 0,
+// three multiply-adds per triangle - d2 = fma(DEN, DEN, m), fma(-aU, aU, d2), fma(-aV, aV, d2) -
+// instead of two subtractions and two multiply-adds: the CUDA-core epilogue, not the tensor pipe,
+// bounds the kernel, so an instruction per pair of triangles less is 10 % of the sweep.
 // Each triangle's three rows are pre-scaled by s = 1/sqrt(G2tc_tri), which turns the margin
 // m = K2_ray * G2tc_tri into the per-RAY constant K2_ray:
-//   candidate  <=>  uN' (DEN' - uN') + K2_ray >= 0  and  vN' (DEN' - vN') + K2_ray >= 0.
+//   candidate  <=>  DEN'^2 + K2_ray - aU'^2 >= 0  and  DEN'^2 + K2_ray - aV'^2 >= 0.
 //
 // Margin.  Measured on B200 (tools/ubench_tmem.cu, profiles/r1_ubench_tmem.txt): a kind::tf32
 // tcgen05.mma sums its K = 8 products and the accumulator with extra bits and truncates once
 // (|err| <= 2.7 u sum|terms| observed per instruction, 6.2 u over three); budget 16 u.  Operand
 // splitting costs <= 4 u per operand, M = O x D in fp32 <= 2 u, the scaled coefficient's
 // rounding <= 1 u: eps_filter <= (16 + 6 + 5) u |D| Emax (|O| + |V0|), plus the reference's own
-// 7 u, times the same 1.5 allowance: eps = 56 u |D| Emax L.  The bound of the fp32 filter above
-// with this eps reads  -(4 u d^2 + 3 eps |d| + 2 eps^2) >= -u |D|^2 Emax L (172 E12 + 6272 u Emax L),
-// so G2tc_tri = Emax (172 E12 + 6272 u Emax Lcap) with the same K2_ray.
+// 7 u, times the same 1.5 allowance: eps = 56 u |D| Emax L bounds |DEN_f - DEN_ref|; the aU / aV
+// rows carry three times the terms, 3 eps.  If the reference accepts, uN_ref and DEN_ref have equal
+// signs and |uN_ref| <= |DEN_ref| (1 + 3u), i.e. |aU_ref| <= |d| (1 + 6u) with d = DEN_ref,
+// |d| <= |D| E12; then
+//   aU_f^2 - DEN_f^2 <= 13 u d^2 + 2 |d| (3 eps + eps)(1 + 6u) + (4 eps)^2,
+// and the two roundings of the epilogue's multiply-adds add <= u DEN_f^2: the test passes whenever
+//   m >= u |D|^2 Emax L (463 E12 + 50176 u Emax L)        (E12^2 <= E12 Emax L was used),
+// which the separable product of K2_ray (above, unchanged) and
+//   G2tc_tri = Emax (463 E12 + 50176 u Emax Lcap)
+// covers with a factor 2 to spare.  (The product form uN (DEN - uN) of the fp32 filter needs
+// 4 x (172 E12 + 6272 u Emax L) in these units: the square form is no wider.)
 LPCL_HD float tf32_rna(float x) // round to nearest (ties away) to 10 explicit mantissa bits, as cvt.rna.tf32.f32
 {
     union { float f; uint32_t u; } v;
@@ -248,7 +263,7 @@ LPCL_HD void tf32_split(float x, float &hi, float &lo)
 }
 
 struct TcRows {
-    float c[3][6]; // rows DEN', uN', vN' over (Mx, My, Mz, Dx, Dy, Dz)
+    float c[3][6]; // rows DEN', aU', aV' over (Mx, My, Mz, Dx, Dy, Dz)
 };
 
 LPCL_HD TcRows make_tc_rows(V3 v0, V3 v1, V3 v2, float vmax)
@@ -258,32 +273,29 @@ LPCL_HD TcRows make_tc_rows(V3 v0, V3 v1, V3 v2, float vmax)
     double ox = v0.x, oy = v0.y, oz = v0.z;
     double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
     double emax = l1 > l2 ? l1 : l2;
-    double g = emax * (172.0 * l1 * l2 + 3.74e-4 * emax * 4.0 * (double)vmax) * 1.001; // 6272 * 2^-24 = 3.738e-4
+    double g = emax * (463.0 * l1 * l2 + 2.991e-3 * emax * 4.0 * (double)vmax) * 1.001; // 50176 * 2^-24 = 2.9907e-3
     double s = 1.0 / sqrt(g > 1e-30 ? g : 1e-30);
+    const double nn[3] = {e2y * e1z - e2z * e1y, e2z * e1x - e2x * e1z, e2x * e1y - e2y * e1x}; // Nn = E2 x E1
+    const double a[3] = {oy * e2z - oz * e2y, oz * e2x - ox * e2z, ox * e2y - oy * e2x};         // A = V0 x E2
+    const double b[3] = {e1y * oz - e1z * oy, e1z * ox - e1x * oz, e1x * oy - e1y * ox};         // B = E1 x V0
+    const double e2d[3] = {e2x, e2y, e2z}, e1d[3] = {e1x, e1y, e1z};
     TcRows r;
-    r.c[0][0] = r.c[0][1] = r.c[0][2] = 0.0f;
-    r.c[0][3] = (float)(s * (e2y * e1z - e2z * e1y)); // Nn
-    r.c[0][4] = (float)(s * (e2z * e1x - e2x * e1z));
-    r.c[0][5] = (float)(s * (e2x * e1y - e2y * e1x));
-    r.c[1][0] = (float)(s * e2x);                     // E2
-    r.c[1][1] = (float)(s * e2y);
-    r.c[1][2] = (float)(s * e2z);
-    r.c[1][3] = (float)(s * (oy * e2z - oz * e2y));   // A = V0 x E2
-    r.c[1][4] = (float)(s * (oz * e2x - ox * e2z));
-    r.c[1][5] = (float)(s * (ox * e2y - oy * e2x));
-    r.c[2][0] = (float)(-s * e1x);                    // E1n
-    r.c[2][1] = (float)(-s * e1y);
-    r.c[2][2] = (float)(-s * e1z);
-    r.c[2][3] = (float)(s * (e1y * oz - e1z * oy));   // B = E1 x V0
-    r.c[2][4] = (float)(s * (e1z * ox - e1x * oz));
-    r.c[2][5] = (float)(s * (e1x * oy - e1y * ox));
+    for (int k = 0; k < 3; ++k) {
+        r.c[0][k] = 0.0f;                                   // DEN = D . Nn
+        r.c[0][3 + k] = (float)(s * nn[k]);
+        r.c[1][k] = (float)(s * 2.0 * e2d[k]);              // aU = 2 (E2 . M + D . A) - D . Nn
+        r.c[1][3 + k] = (float)(s * (2.0 * a[k] - nn[k]));
+        r.c[2][k] = (float)(-s * 2.0 * e1d[k]);             // aV = 2 (-E1 . M + D . B) - D . Nn
+        r.c[2][3 + k] = (float)(s * (2.0 * b[k] - nn[k]));
+    }
     return r;
 }
 
 // Host model of the tensor-core filter for the property test: the three GEMM outputs are formed
 // exactly from the split operands (double), then pushed by +-16 u sum|terms| in the direction
-// `push` selects (bit 0: DEN', bit 1: uN', bit 2: vN'); the caller requires a reference hit to be a
-// candidate for every push.  Not used on the GPU.
+// `push` selects (bit 0: DEN', bit 1: aU', bit 2: aV'); the caller requires a reference hit to be a
+// candidate for every push.  The epilogue's three multiply-adds are evaluated as the GPU does.
+// Not used on the GPU.
 LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, float mx, float my, float mz, float k2, int push)
 {
     const float a[6] = {mx, my, mz, dx, dy, dz};
@@ -301,8 +313,9 @@ LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, 
         const double e = 16.0 * 5.9604644775390625e-8 * sabs;
         out[r] = (float)(s + (((push >> r) & 1) ? e : -e));
     }
-    const float pu = LPCL_FMA(out[1], LPCL_SUB(out[0], out[1]), k2);
-    const float pv = LPCL_FMA(out[2], LPCL_SUB(out[0], out[2]), k2);
+    const float d2 = LPCL_FMA(out[0], out[0], k2);
+    const float pu = LPCL_FMA(-out[1], out[1], d2);
+    const float pv = LPCL_FMA(-out[2], out[2], d2);
     return !(signbit(pu) || signbit(pv));
 }
 

@@ -5,14 +5,14 @@
 // atomicAdd into the mesh-major scratch.  What changes is who evaluates the conservative filter
 // (lpcl_math.cuh, "the same filter evaluated by the tensor cores"):
 //
-//   D[128 rays][192] = A[128 rays][K = 24] . B[64 triangles x {DEN', uN', vN'}][K = 24]^T
+//   D[128 rays][192] = A[128 rays][K = 24] . B[64 triangles x {DEN', aU', aV'}][K = 24]^T
 //
 // is three kind::tf32 tcgen05.mma (M = 128, N = 192, K = 8) per (ray tile, triangle tile); the 24
 // K-slots carry the four partial products of the hi/lo TF32 split of the six ray numbers (M, D)
 // and of the triangle's scaled coefficients.  The accumulator lives in TMEM (two 192-column
 // buffers, so the MMAs of the next ray tile overlap the epilogue of this one); the epilogue warps
 // read it back with tcgen05.ld (lane = ray, 6 consecutive columns = one pair of triangles), apply
-// the two sign-agnostic product tests with packed FP32 (2 x sub.f32x2 + 2 x fma.rn.f32x2 + 2 x LOP3
+// the two sign-agnostic tests in their square form with packed FP32 (3 x fma.rn.f32x2 + 2 x LOP3
 // per PAIR of triangles - the 15 FMAs per test of the SIMT kernel are gone) and hand the rare
 // candidates to the exact, reference-ordered evaluation, which alone decides results.
 //
@@ -37,6 +37,34 @@
 #include "lpcl_search.cuh"
 
 namespace lpcl {
+
+#ifndef LPCL_TC_TRIM
+#define LPCL_TC_TRIM 1   // uniform warp index, elected arrive, vote-uniform candidate branch (experiment switch)
+#endif
+#ifndef LPCL_TC_VOTE
+#define LPCL_TC_VOTE LPCL_TC_TRIM   // candidate branch on a warp vote (uniform) instead of per lane (experiment switch)
+#endif
+#ifndef LPCL_TC_PROBE
+#define LPCL_TC_PROBE 0  // probe the next accumulator's "full" barrier before the first chunk test (experiment switch)
+#endif
+#ifndef LPCL_TC_SKEW
+#define LPCL_TC_SKEW 0   // one-time start delay (SM cycles) of the epilogue warps of half 1 (experiment switch)
+#endif
+
+#ifdef LPCL_TC_TRACE
+// development build only: clock64 stamps of CTA (0,0)'s epilogue warps 0 and 4 (one SM sub-partition) and of the MMA
+// warp at the segment boundaries of steps [TC_TRACE_FIRST, TC_TRACE_FIRST + TC_TRACE_STEPS); read back with
+// lpcl_debug_read_trace (tools/kbench.py --trace)
+constexpr int TC_TRACE_FIRST = 400, TC_TRACE_STEPS = 48, TC_TRACE_SLOTS = 8;
+__device__ long long g_tc_trace[3][TC_TRACE_STEPS][TC_TRACE_SLOTS];
+#define TC_STAMP(who, step, slot)                                                                                     \
+    do {                                                                                                              \
+        if (trace_on && (step) >= TC_TRACE_FIRST && (step) < TC_TRACE_FIRST + TC_TRACE_STEPS && (threadIdx.x & 31) == 0) \
+            g_tc_trace[who][(step) - TC_TRACE_FIRST][slot] = clock64();                                             \
+    } while (0)
+#else
+#define TC_STAMP(who, step, slot) do {} while (0)
+#endif
 
 constexpr int TC_TILE_TRIS = 64;                       // triangles per B tile
 constexpr int TC_N = 3 * TC_TILE_TRIS;                 // 192 accumulator columns
@@ -134,6 +162,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool tc_elect_one()
 {
@@ -281,10 +319,20 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     uint64_t *tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA issuer)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+#if LPCL_TC_TRIM
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived
+    // from it (TMEM addresses, queue pointers, role branches) in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#else
+    const int warp = tid >> 5;
+#endif
     const int c0 = blockIdx.y * tiles_per_chunk;
     const int c1 = min(c0 + tiles_per_chunk, sc.tc_n_tiles);
     const int nt = max(c1 - c0, 0);
+#ifdef LPCL_TC_TRACE
+    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0;
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -365,7 +413,9 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
 #pragma unroll
             for (int j = 0; j < RT; ++j, ++g) {
                 const int buf = g & 1, use = g >> 1;
+                TC_STAMP(2, g, 0);
                 if (use > 0) mbar_wait(&tempty_bar[buf], (unsigned)((use - 1) & 1));
+                TC_STAMP(2, g, 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
                 const uint64_t da = a_desc0 + (uint64_t)((j * TC_A_BYTES) >> 4);
@@ -377,6 +427,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                     if (j == RT - 1) tc_commit(&empty_bar[s]); // the tile's shared-memory slot is free once its MMAs completed
                 }
                 __syncwarp();
+                TC_STAMP(2, g, 2);
             }
         }
     } else {
@@ -388,37 +439,54 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
         const int steps = nt * RT;
         uint32_t rA[48], rB[48];
 
-        // the two product tests on 16 triangles x this lane's ray; candidates go to the warp's queue
-        auto test_chunk = [&](const uint32_t(&r)[48], u64 kk, int first, int tri0, int count, int mesh, long long i) {
-            u64 du[8], dv[8];
+        // the two tests on 16 triangles x this lane's ray in the square form (lpcl_math.cuh):
+        //   d2 = DEN'^2 + K2,  du = d2 - aU'^2,  dv = d2 - aV'^2   (three FFMA2 per PAIR of triangles; the
+        // negations are operand modifiers); a negative du or dv = not a candidate.  Candidates go to the warp's queue
+        auto test_chunk = [&](const uint32_t(&r)[48], float2 kk, int first, int tri0, int count, int mesh, long long i) {
+            float2 du[8], dv[8];
             unsigned none[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}; // a sign bit survives only if every test failed
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const u64 den = pack2(r[6 * q + 0], r[6 * q + 1]);
-                const u64 un = pack2(r[6 * q + 2], r[6 * q + 3]);
-                const u64 vn = pack2(r[6 * q + 4], r[6 * q + 5]);
-                du[q] = ffma2(un, fsub2(den, un), kk); // uN' (DEN' - uN') + K2
-                dv[q] = ffma2(vn, fsub2(den, vn), kk); // vN' (DEN' - vN') + K2
-                none[(2 * q) & 3] = or_and(lo32(du[q]), lo32(dv[q]), none[(2 * q) & 3]);
-                none[(2 * q + 1) & 3] = or_and(hi32(du[q]), hi32(dv[q]), none[(2 * q + 1) & 3]);
+                const float2 den = make_float2(__uint_as_float(r[6 * q + 0]), __uint_as_float(r[6 * q + 1]));
+                const float2 au = make_float2(__uint_as_float(r[6 * q + 2]), __uint_as_float(r[6 * q + 3]));
+                const float2 av = make_float2(__uint_as_float(r[6 * q + 4]), __uint_as_float(r[6 * q + 5]));
+                const float2 d2 = __ffma2_rn(den, den, kk);
+                du[q] = __ffma2_rn(make_float2(-au.x, -au.y), au, d2);
+                dv[q] = __ffma2_rn(make_float2(-av.x, -av.y), av, d2);
+                none[(2 * q) & 3] = or_and(__float_as_uint(du[q].x), __float_as_uint(dv[q].x), none[(2 * q) & 3]);
+                none[(2 * q + 1) & 3] = or_and(__float_as_uint(du[q].y), __float_as_uint(dv[q].y), none[(2 * q + 1) & 3]);
             }
-            if ((int)(none[0] & none[1] & none[2] & none[3]) >= 0) { // rare: a triangle of the chunk passed both tests
-                // sign bits (1 = failed) funnel-shifted in from triangle 15 down to 0: bit t of `failed` = triangle t
-                unsigned failed = 0;
+            const bool some = (int)(none[0] & none[1] & none[2] & none[3]) >= 0; // rare: a triangle of the chunk passed both tests
+#if LPCL_TC_VOTE
+            if (__any_sync(0xffffffffu, some)) { // warp-uniform branch: the common path carries no reconvergence code
+                if (some) {
+#else
+            {
+                if (some) {
+#endif
+                    // sign bits (1 = failed) funnel-shifted in from triangle 15 down to 0: bit t of `failed` = triangle t
+                    unsigned failed = 0;
 #pragma unroll
-                for (int q = 7; q >= 0; --q) {
-                    failed = __funnelshift_l(hi32(du[q]) | hi32(dv[q]), failed, 1);
-                    failed = __funnelshift_l(lo32(du[q]) | lo32(dv[q]), failed, 1);
+                    for (int q = 7; q >= 0; --q) {
+                        failed = __funnelshift_l(__float_as_uint(du[q].y) | __float_as_uint(dv[q].y), failed, 1);
+                        failed = __funnelshift_l(__float_as_uint(du[q].x) | __float_as_uint(dv[q].x), failed, 1);
+                    }
+                    unsigned mask = ~failed & 0xffffu;
+                    const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
+                    if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
+                    n_cand += __popc(mask);
+                    if (mask && i < rays.n) tc_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
                 }
-                unsigned mask = ~failed & 0xffffu;
-                const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
-                if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
-                n_cand += __popc(mask);
-                if (mask && i < rays.n) tc_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
+                __syncwarp(); // reconverge: tcgen05.ld and the barrier hand-shake are warp-collective
             }
-            __syncwarp(); // reconverge: tcgen05.ld and the barrier hand-shake are warp-collective
         };
 
+#if LPCL_TC_SKEW > 0
+        if (half == 1) { // start the two warps of every SM sub-partition out of phase (they share its issue port)
+            const long long t0 = clock64();
+            while (clock64() - t0 < LPCL_TC_SKEW) {}
+        }
+#endif
         if (steps > 0) { // prologue: step 0 into both buffers
             mbar_wait(&tfull_bar[0], 0u);
             tc_fence_after();
@@ -426,7 +494,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             tc_ld_48(lane_addr + 48u, rB);
         }
         int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
-        u64 k2s[RT];
+        float2 k2s[RT];
         int vc_bits = 0; // Vc is a positive float: the first tile always differs
         for (int it = 0; it < nt; ++it) {
             const int4 ti4 = ti_next; // fetched one tile ahead: the L2 latency is off the critical path
@@ -438,30 +506,50 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
 #pragma unroll
                 for (int j = 0; j < RT; ++j) {
                     const float kk = filter_ray_scale_tile(rs[j], two_vc, inv_four_vc);
-                    k2s[j] = pack2(__float_as_uint(kk), __float_as_uint(kk));
+                    k2s[j] = make_float2(kk, kk);
                 }
             }
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
                 const int g = it * RT + j, buf = g & 1;
-                const u64 k2 = k2s[j];
+                const float2 k2 = k2s[j];
                 const bool more = g + 1 < steps;
                 const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
                 const long long i = ray0 + (long long)j * TC_M;
+                TC_STAMP(half, g, 0);
                 tc_wait_ld(); // both chunks of step g are in registers: hand the accumulator back
+                TC_STAMP(half, g, 1);
                 tc_fence_before();
                 __syncwarp();
+#if LPCL_TC_TRIM
+                if (tc_elect_one()) mbar_arrive(&tempty_bar[buf]);
+#else
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+#endif
                 if (j == 0 && *(volatile int *)q_count >= TC_QUEUE_DRAIN) // once per triangle tile; an overflowing append evaluates in place
                     tc_drain(queue, q_count, sc, rays, eps, key, cnt);
+                TC_STAMP(half, g, 2);
+#if LPCL_TC_PROBE
+                // the accumulator of step g + 1 is almost always complete by now (the MMAs run a step ahead): probe its
+                // barrier here so that the probe's latency hides behind the first chunk test
+                const bool next_ready = more && mbar_test(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
+#endif
                 test_chunk(rA, k2, chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                TC_STAMP(half, g, 3);
                 if (more) { // the first chunk of step g + 1 loads while the second chunk of step g is tested
+#if LPCL_TC_PROBE
+                    if (!next_ready)
+#endif
                     mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
+                    TC_STAMP(half, g, 4);
                     tc_fence_after();
                     tc_ld_48(next_addr, rA);
                 }
+                TC_STAMP(half, g, 5);
                 test_chunk(rB, k2, (chunk0 + 1) * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                TC_STAMP(half, g, 6);
                 if (more) tc_ld_48(next_addr + 48u, rB);
+                TC_STAMP(half, g, 7);
             }
         }
         tc_drain(queue, q_count, sc, rays, eps, key, cnt);
