@@ -38,19 +38,6 @@
 
 namespace lpcl {
 
-#ifndef LPCL_TC_TRIM
-#define LPCL_TC_TRIM 1   // uniform warp index, elected arrive, vote-uniform candidate branch (experiment switch)
-#endif
-#ifndef LPCL_TC_VOTE
-#define LPCL_TC_VOTE LPCL_TC_TRIM   // candidate branch on a warp vote (uniform) instead of per lane (experiment switch)
-#endif
-#ifndef LPCL_TC_PROBE
-#define LPCL_TC_PROBE 0  // probe the next accumulator's "full" barrier before the first chunk test (experiment switch)
-#endif
-#ifndef LPCL_TC_SKEW
-#define LPCL_TC_SKEW 0   // one-time start delay (SM cycles) of the epilogue warps of half 1 (experiment switch)
-#endif
-
 #ifdef LPCL_TC_TRACE
 // development build only: clock64 stamps of CTA (0,0)'s epilogue warps 0 and 4 (one SM sub-partition) and of the MMA
 // warp at the segment boundaries of steps [TC_TRACE_FIRST, TC_TRACE_FIRST + TC_TRACE_STEPS); read back with
@@ -162,16 +149,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// non-blocking probe of an mbarrier phase
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool tc_elect_one()
 {
@@ -232,6 +209,9 @@ struct ExactLimits {
 __device__ __forceinline__ void tc_exact_one(const SceneDev &sc, const RaysDev &rays, long long i, int tri, int mesh, ExactLimits lim,
                                              unsigned long long *key, int *cnt)
 {
+#ifdef LPCL_TC_NOEXACT // timing experiment only: results are wrong
+    return;
+#endif
     const long long ph = rays.phys(i);
     const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
     const float4 a = __ldg(sc.v0 + tri), b = __ldg(sc.v1 + tri), c = __ldg(sc.v2 + tri);
@@ -320,13 +300,10 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
     const int tid = threadIdx.x, lane = tid & 31;
-#if LPCL_TC_TRIM
     // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived
-    // from it (TMEM addresses, queue pointers, role branches) in uniform registers
+    // from it (TMEM addresses, queue pointers, role branches) in uniform registers (LDTM with a uniform base and
+    // immediate offsets instead of two R2UR per load: +20 % together with the elected arrive and the vote below)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-#else
-    const int warp = tid >> 5;
-#endif
     const int c0 = blockIdx.y * tiles_per_chunk;
     const int c1 = min(c0 + tiles_per_chunk, sc.tc_n_tiles);
     const int nt = max(c1 - c0, 0);
@@ -457,21 +434,19 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 none[(2 * q + 1) & 3] = or_and(__float_as_uint(du[q].y), __float_as_uint(dv[q].y), none[(2 * q + 1) & 3]);
             }
             const bool some = (int)(none[0] & none[1] & none[2] & none[3]) >= 0; // rare: a triangle of the chunk passed both tests
-#if LPCL_TC_VOTE
             if (__any_sync(0xffffffffu, some)) { // warp-uniform branch: the common path carries no reconvergence code
                 if (some) {
-#else
-            {
-                if (some) {
-#endif
-                    // sign bits (1 = failed) funnel-shifted in from triangle 15 down to 0: bit t of `failed` = triangle t
-                    unsigned failed = 0;
+                    // sign bits (1 = failed) funnel-shifted in from the top triangle down, as two independent chains:
+                    // bit t of f_lo = triangle t, bit t of f_hi = triangle 8 + t
+                    unsigned f_lo = 0, f_hi = 0;
 #pragma unroll
-                    for (int q = 7; q >= 0; --q) {
-                        failed = __funnelshift_l(__float_as_uint(du[q].y) | __float_as_uint(dv[q].y), failed, 1);
-                        failed = __funnelshift_l(__float_as_uint(du[q].x) | __float_as_uint(dv[q].x), failed, 1);
+                    for (int q = 3; q >= 0; --q) {
+                        f_lo = __funnelshift_l(__float_as_uint(du[q].y) | __float_as_uint(dv[q].y), f_lo, 1);
+                        f_hi = __funnelshift_l(__float_as_uint(du[q + 4].y) | __float_as_uint(dv[q + 4].y), f_hi, 1);
+                        f_lo = __funnelshift_l(__float_as_uint(du[q].x) | __float_as_uint(dv[q].x), f_lo, 1);
+                        f_hi = __funnelshift_l(__float_as_uint(du[q + 4].x) | __float_as_uint(dv[q + 4].x), f_hi, 1);
                     }
-                    unsigned mask = ~failed & 0xffffu;
+                    unsigned mask = ~((f_lo & 0xffu) | (f_hi << 8)) & 0xffffu;
                     const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
                     if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
                     n_cand += __popc(mask);
@@ -481,12 +456,6 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             }
         };
 
-#if LPCL_TC_SKEW > 0
-        if (half == 1) { // start the two warps of every SM sub-partition out of phase (they share its issue port)
-            const long long t0 = clock64();
-            while (clock64() - t0 < LPCL_TC_SKEW) {}
-        }
-#endif
         if (steps > 0) { // prologue: step 0 into both buffers
             mbar_wait(&tfull_bar[0], 0u);
             tc_fence_after();
@@ -521,25 +490,13 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 TC_STAMP(half, g, 1);
                 tc_fence_before();
                 __syncwarp();
-#if LPCL_TC_TRIM
                 if (tc_elect_one()) mbar_arrive(&tempty_bar[buf]);
-#else
-                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-#endif
                 if (j == 0 && *(volatile int *)q_count >= TC_QUEUE_DRAIN) // once per triangle tile; an overflowing append evaluates in place
                     tc_drain(queue, q_count, sc, rays, eps, key, cnt);
                 TC_STAMP(half, g, 2);
-#if LPCL_TC_PROBE
-                // the accumulator of step g + 1 is almost always complete by now (the MMAs run a step ahead): probe its
-                // barrier here so that the probe's latency hides behind the first chunk test
-                const bool next_ready = more && mbar_test(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
-#endif
                 test_chunk(rA, k2, chunk0 * TC_CHUNK_TRIS, tri0, count, mesh, i);
                 TC_STAMP(half, g, 3);
                 if (more) { // the first chunk of step g + 1 loads while the second chunk of step g is tested
-#if LPCL_TC_PROBE
-                    if (!next_ready)
-#endif
                     mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
                     TC_STAMP(half, g, 4);
                     tc_fence_after();
