@@ -57,6 +57,15 @@ static inline float pown(float x, int n) {
     return r;
 }
 
+/* OpenCL C with cl_khr_fp64 also has double pown(double, int): `pown((1.0 + pown(xt,2) + pown(yt,2)), 2)` in
+ * stereograph_project (.cl:501) squares a DOUBLE (the literal 1.0 promotes the sum).  Every pown on
+ * the hot path has a float argument and keeps resolving to the float overload above. */
+static inline double pown(double x, int n) {
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r = r * x;
+    return r;
+}
+
 extern thread_local int lpcl_shim_gid;
 static inline int get_global_id(int) { return lpcl_shim_gid; }
 

@@ -14,6 +14,13 @@ Two interchangeable kernel backends, same call signatures:
                  Pinned bit-for-bit to ``"reference"`` by tests/test_oracle_pinning.py.
 (``"reference_fast"`` / ``"port_fast"`` are the -O3 timing builds of the same sources.)
 
+``project()`` / ``bin2d()`` check the measured-ray post-processing:
+``"reference"`` = oracle/_ref/libref_proj.so, the reference's own ``stereograph_project`` /
+``angular_project`` kernels (.cl:488-538) compiled from the reference source (its OpenCL vector
+literals rewritten on the fly, see proj_shim.cpp); ``"port"`` = the NumPy restatement below,
+pinned to it by tests/test_oracle_projection.py.  ``bin2d`` is ``np.histogram2d`` exactly as the
+reference calls it (it:416,529,560).
+
 On top of the kernels, ``trace()`` restates the reference's host loop
 (iterative_tracer.py:77-393): source/mesh flattening (it:99-151), the three launches per
 generation (it:288/303/318; the <=50,000-ray chunking of it:218-273 is omitted because rays
@@ -31,6 +38,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS = {
+    "reference_proj": os.path.join(HERE, "_ref", "libref_proj.so"),
     "reference": os.path.join(HERE, "_ref", "libref_strict.so"),
     "reference_fast": os.path.join(HERE, "_ref", "libref_fast.so"),
     "port": os.path.join(HERE, "_build", "liboracle_port.so"),
@@ -320,3 +328,77 @@ def measured_rays(results):
             pos = np.concatenate((pos, d), axis=0)
             pwr = np.concatenate((pwr.flatten(), q.flatten()), axis=0)
     return pos, pwr
+
+
+# ----------------------------------------------------------------------------- measured-ray post-processing
+_F = np.float32
+PROJECTIONS = ("xy", "stereographic", "angular")
+
+
+def _project_reference(kind, pos, pwr, rot):
+    """The reference kernels themselves (libref_proj.so), launched like it:515 / it:546: pivot (0,0,0,0),
+    R = the 4x4 float32 matrix whose upper-left 3x3 is `rot` (identity by default, it:514,545)."""
+    lib = _lib("reference_proj")
+    n = len(pwr)
+    vecs = np.ascontiguousarray(np.asarray(pos, dtype=_F).reshape(-1, 4))
+    r4 = np.zeros((4, 4), dtype=_F)
+    r4[:3, :3] = np.eye(3, dtype=_F) if rot is None else np.asarray(rot, dtype=_F)[:3, :3]
+    pivot = np.zeros((1, 4), dtype=_F)
+    x, y, w = (np.zeros(n, dtype=_F) for _ in range(3))
+    fn = lib.ref_launch_stereograph_project if kind == "stereographic" else lib.ref_launch_angular_project
+    fn(C.c_int(n), _f(vecs), _f(pwr), _f(r4), _f(pivot), _f(x), _f(y), _f(w))
+    return x, y, w
+
+
+def _project_port(kind, pos, pwr, rot):
+    """NumPy restatement of .cl:488-538: float32 in the kernels' operation order, double where OpenCL C
+    promotes (the literals 1.0 / 4.0 of .cl:501)."""
+    p = np.asarray(pos, dtype=_F)[:, :3]
+    r = np.eye(3, dtype=_F) if rot is None else np.asarray(rot, dtype=_F)[:3, :3]
+    # dot(vec, rot_mtx[k]) = (x*r0 + y*r1) + z*r2, each product and sum rounded to float32 (pivot = 0)
+    u, v, w = [(p[:, 0] * r[k, 0] + p[:, 1] * r[k, 1]) + p[:, 2] * r[k, 2] for k in range(3)]
+    l = np.sqrt((u * u + v * v) + w * w, dtype=_F)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if kind == "stereographic":  # .cl:499-505
+            xt = u / (l + w)
+            yt = v / (l + w)
+            s = (1.0 + (xt * xt).astype(np.float64)) + (yt * yt).astype(np.float64)
+            a = (4.0 / (s * s)).astype(_F)
+            return xt.astype(_F), yt.astype(_F), (pwr / a).astype(_F)
+        # angular, .cl:519-537: vecr = (u,v,w)/l; cosT = dot((0,0,1), vecr) = (0*x + 0*y) + 1*z
+        cos_t = (_F(0) * (u / l) + _F(0) * (v / l)) + _F(1) * (w / l)
+        phi = np.arctan2(v, u, dtype=_F)
+        rr = np.arccos(cos_t, dtype=_F)
+        xt = rr * np.cos(phi, dtype=_F)
+        yt = rr * np.sin(phi, dtype=_F)
+        a = np.ones_like(rr)
+        big = rr > _F(0.000001)
+        a[big] = np.sin(rr[big], dtype=_F) / rr[big]
+        return xt.astype(_F), yt.astype(_F), (pwr / a).astype(_F)
+
+
+def project(kind, pos, pwr, rot=None, backend=None):
+    """-> (x, y, corrected power), float32, like the reference kernels' x / y / pwrs_cor buffers
+    (kind "xy": the plain x, y, power that get_binned_data bins, it:413-418)."""
+    pwr = np.ascontiguousarray(np.asarray(pwr, dtype=_F).reshape(-1))
+    if kind == "xy":
+        p = np.asarray(pos, dtype=_F)
+        return p[:, 0].copy(), p[:, 1].copy(), pwr
+    if kind not in PROJECTIONS:
+        raise ValueError("unknown projection %r" % (kind,))
+    if backend is None:
+        backend = "reference" if available("reference_proj") else "port"
+    return (_project_reference if backend == "reference" else _project_port)(kind, pos, pwr, rot)
+
+
+def bin2d(x, y, w, limits, points, kind):
+    """np.histogram2d exactly as the reference calls it: raw weights for get_binned_data (it:416),
+    float64(pwr) / (dx * dy) for the two projections (it:525-529, 556-560)."""
+    if kind == "xy":
+        weights = np.asarray(w)
+    else:
+        dx = np.float64(limits[0][1] - limits[0][0]) / np.float64(points)
+        dy = np.float64(limits[1][1] - limits[1][0]) / np.float64(points)
+        weights = np.float64(w) / (dx * dy)
+    return np.histogram2d(x=np.asarray(x).flatten(), y=np.asarray(y).flatten(), bins=points, range=limits,
+                          weights=np.asarray(weights).flatten())
