@@ -42,7 +42,11 @@ def _worker(rank, world, port, scene_name, kw, out_dir):
 
 
 @pytest.mark.parametrize("scene_name,kw", [("c2_directivity_lens", dict(ray_count=3001)),
-                                           ("c4_human_eye", dict(ray_count=150, sources=2, trace_iterations=6))])
+                                           ("c4_human_eye", dict(ray_count=150, sources=2, trace_iterations=6)),
+                                           # 40 generations: past the 31 branch bits of a lineage id (dist.renumber_lineage)
+                                           ("glass_cube_cavity", dict(ray_count=301, trace_iterations=40)),
+                                           # fewer rays than ranks: rank 0 traces nothing and still takes part in the gather
+                                           ("glass_cube_cavity", dict(ray_count=1, trace_iterations=5))])
 def test_two_gpu_trace_equals_oracle(tmp_path, scene_name, kw):
     import torch
     import torch.multiprocessing as mp
