@@ -77,9 +77,18 @@ def report(path, out_dir, tag, note):
         rd = float(rec["dram__bytes_read.sum"].replace(",", "")) * UNIT.get(u["dram__bytes_read.sum"], 1)
         wr = float(rec["dram__bytes_write.sum"].replace(",", "")) * UNIT.get(u["dram__bytes_write.sum"], 1)
         dur = float(rec["gpu__time_duration.sum"].replace(",", ""))
+        def pct(key):
+            try:
+                return float(rec[key].replace(",", ""))
+            except Exception:
+                return None
+
         traffic.setdefault(short, []).append({"dram_read_bytes": rd, "dram_write_bytes": wr,
                                               "duration": dur, "duration_unit": u["gpu__time_duration.sum"],
-                                              "grid": rec["launch__grid_size"]})
+                                              "grid": rec["launch__grid_size"],
+                                              "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                                              "tensor_pipe_pct": pct("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                                              "issue_pct": pct("sm__inst_issued.avg.pct_of_peak_sustained_active")})
         with open(os.path.join(out_dir, "%s_%s_%d_ncu.txt" % (tag, short, k)), "w") as f:
             f.write("# %s\n# kernel: %s (launch %d of this kernel in the capture)\n" % (note, rec["Kernel Name"][:200], k))
             for h in hdr:
