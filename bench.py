@@ -322,6 +322,10 @@ def main_native(args):
             acc["launches"] += tr.kernel_launches
             acc["rays"] += sum(tr.stats["rays"])
             # rank-LOCAL parents and surviving children of every generation (132 B + 44 B)
+            if tr.stats.get("one_launch_generations"):  # small scene traced in one launch: no per-generation kernels
+                acc["search_ms"] += sum(kt["search_ms"] for kt in tr.kernel_times)
+                acc["n_search"] += len(tr.kernel_times)
+                continue
             for kt, live_local in zip(tr.kernel_times, [x for x, n in zip(tr.stats["live_local"], tr.stats["rays"]) if n]):
                 acc["search_ms"] += kt["search_ms"]
                 acc["resolve_ms"] += kt["resolve_ms"]

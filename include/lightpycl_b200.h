@@ -190,6 +190,43 @@ int lpcl_trace_resolve(const lpcl_scene *scene, const lpcl_generation *parents, 
                        int64_t measured_base, int64_t measured_capacity, lpcl_step_counters *d_counters,
                        void *d_workspace, float max_ray_len, float ior_env, int32_t iteration, void *stream);
 
+/* ---------------------------------------------------------------- small scenes: the whole trace in one launch
+ * Replaces the complete host loop iterative_tracer.py:241-391 (every generation, both termination
+ * tests it:383-391) for scenes of the size of the reference's example_nested_cubes_refraction.py
+ * (10 rays x 48 triangles): one CTA runs the generations back to back, the caller reads the table
+ * once.  Bit-identical to the general path (same device functions; unfiltered exact search).
+ *
+ * Arena: d_org_pow / d_dir_prev (/ d_lineage) hold `arena_rays` ray slots in the packed layout above;
+ * the caller packs generation 0 (n0 rays) at slot 0 (lpcl_pack_rays).  Generation k occupies the
+ * region [offset_k, offset_k + cap_k), cap_0 = n0, cap_{k+1} = 2 n_k, in the two-segment layout
+ * (seg_split = n_reflect of its parents, seg_base = n of its parents); its per-ray results go to
+ * d_dest_meas / d_hit at slots offset_k + logical ray index.  d_scratch: lpcl_small_scratch_bytes(scene,
+ * scratch_rays) bytes.  Measured parents are appended to d_measured_out from record 0.
+ * The kernel processes at most min(max_iterations, 31) generations and stops BEFORE one that has more
+ * than pair_limit ray x triangle pairs, more than scratch_rays rays, or does not fit the arena / the
+ * measured buffer: d_header then says stop_reason = 1 and describes the generation to continue with
+ * (lpcl_trace_search / lpcl_trace_resolve on the same arena buffers).  power_threshold =
+ * (1 - trace_until_dissipated) * input_power (it:383). */
+typedef struct lpcl_small_iter {
+    int64_t n_rays, n_reflect, n_refract, n_measured, n_terminated;
+    int64_t offset;          /* arena slot of the generation's region */
+    double live_power, measured_power;
+} lpcl_small_iter;
+
+typedef struct lpcl_small_header {
+    int64_t iterations;      /* generations processed (rows of d_iters that are valid) */
+    int64_t stop_reason;     /* 0: the trace ended; 1: handed over before generation `iterations` */
+    int64_t next_offset, next_n, next_split, next_base; /* that generation: region, ray count, seg_split, seg_base */
+    int64_t measured_total, reserved;
+} lpcl_small_header;
+
+int64_t lpcl_small_scratch_bytes(const lpcl_scene *scene, int64_t scratch_rays);
+int lpcl_trace_small(const lpcl_scene *scene, float *d_org_pow, float *d_dir_prev, uint64_t *d_lineage, float *d_dest_meas,
+                     int32_t *d_hit, int64_t arena_rays, int64_t n0, void *d_scratch, int64_t scratch_rays,
+                     float *d_measured_out, uint64_t *d_measured_lineage, int64_t measured_capacity, float max_ray_len,
+                     float ior_env, int32_t max_iterations, double power_threshold, int64_t pair_limit,
+                     lpcl_small_iter *d_iters, lpcl_small_header *d_header, void *stream);
+
 /* Pack / unpack helpers between the reference layout and the packed generation layout. */
 int lpcl_pack_rays(const float *d_origin, const float *d_dir, const float *d_power, const int32_t *d_prev_mesh,
                    int64_t n, int64_t lineage_base, float *d_org_pow, float *d_dir_prev, uint64_t *d_lineage,

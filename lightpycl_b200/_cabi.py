@@ -47,6 +47,21 @@ class Generation(C.Structure):
     ]
 
 
+class SmallIter(C.Structure):
+    """Mirror of ``lpcl_small_iter``."""
+
+    _fields_ = [("n_rays", C.c_int64), ("n_reflect", C.c_int64), ("n_refract", C.c_int64), ("n_measured", C.c_int64),
+                ("n_terminated", C.c_int64), ("offset", C.c_int64), ("live_power", C.c_double),
+                ("measured_power", C.c_double)]
+
+
+class SmallHeader(C.Structure):
+    """Mirror of ``lpcl_small_header``."""
+
+    _fields_ = [("iterations", C.c_int64), ("stop_reason", C.c_int64), ("next_offset", C.c_int64), ("next_n", C.c_int64),
+                ("next_split", C.c_int64), ("next_base", C.c_int64), ("measured_total", C.c_int64), ("reserved", C.c_int64)]
+
+
 # every symbol include/lightpycl_b200.h declares: (restype, argtypes)
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -70,6 +85,9 @@ SYMBOLS = {
                                      _p, _f, _f, _i32, _p]),
     "lpcl_trace_search": (C.c_int, [_p, C.POINTER(Generation), _p, _f, _p, _p]),
     "lpcl_pack_rays": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
+    "lpcl_small_scratch_bytes": (_i64, [_p, _i64]),
+    "lpcl_trace_small": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i64, _f, _f, _i32, C.c_double, _i64,
+                                   _p, _p, _p]),
     "lpcl_project": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _p, _p]),
     "lpcl_bin2d": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i32, C.c_double, _p, _p]),
 }

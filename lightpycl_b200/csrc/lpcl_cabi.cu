@@ -13,6 +13,7 @@
 #include "lpcl_material.cuh"
 #include "lpcl_search_exact.cuh"
 #include "lpcl_search_tc.cuh"
+#include "lpcl_small.cuh"
 
 using namespace lpcl;
 
@@ -67,6 +68,8 @@ struct lpcl_scene {
 };
 
 static_assert(sizeof(StepCounters) == sizeof(lpcl_step_counters), "counter structs must match");
+static_assert(sizeof(SmallIter) == sizeof(lpcl_small_iter) && sizeof(SmallHeader) == sizeof(lpcl_small_header),
+              "small-trace structs must match");
 
 extern "C" int lpcl_abi_version(void) { return LPCL_ABI_VERSION; }
 extern "C" const char *lpcl_last_error(void) { return g_err; }
@@ -552,6 +555,38 @@ extern "C" int lpcl_trace_step(const lpcl_scene *s, const lpcl_generation *paren
     return lpcl_trace_resolve(s, parents, children, d_dest_meas, d_hit, d_measured_out, d_measured_lineage,
                               measured_base, measured_capacity, d_counters, d_workspace, max_ray_len, ior_env, iteration,
                               stream_);
+}
+
+// ------------------------------------------------------------------------------------------ small scenes
+extern "C" int64_t lpcl_small_scratch_bytes(const lpcl_scene *s, int64_t scratch_rays)
+{
+    if (!s || scratch_rays < 0) return 0;
+    return align_up((int64_t)s->dev.mesh_count * scratch_rays * 8, 256) + align_up((int64_t)s->dev.mesh_count * scratch_rays * 4, 256);
+}
+
+extern "C" int lpcl_trace_small(const lpcl_scene *s, float *d_org_pow, float *d_dir_prev, uint64_t *d_lineage, float *d_dest_meas,
+                                int32_t *d_hit, int64_t arena_rays, int64_t n0, void *d_scratch, int64_t scratch_rays,
+                                float *d_measured_out, uint64_t *d_measured_lineage, int64_t measured_capacity, float max_ray_len,
+                                float ior_env, int32_t max_iterations, double power_threshold, int64_t pair_limit,
+                                lpcl_small_iter *d_iters, lpcl_small_header *d_header, void *stream_)
+{
+    if (!s || !d_org_pow || !d_dir_prev || !d_dest_meas || !d_scratch || !d_iters || !d_header)
+        return fail(LPCL_E_NULL, "lpcl_trace_small: NULL argument");
+    if (n0 <= 0 || arena_rays < n0 || scratch_rays <= 0 || max_iterations <= 0)
+        return fail(LPCL_E_RANGE, "lpcl_trace_small: need n0 > 0, arena_rays >= n0, scratch_rays > 0, max_iterations > 0");
+    if (s->dev.mesh_count > SMALL_MAX_MESHES * 1024) return fail(LPCL_E_RANGE, "lpcl_trace_small: too many meshes");
+    if (!aligned16(d_org_pow) || !aligned16(d_dir_prev) || !aligned16(d_dest_meas) || (d_hit && !aligned16(d_hit)) ||
+        (d_measured_out && !aligned16(d_measured_out)))
+        return fail(LPCL_E_ALIGN, "lpcl_trace_small: buffers must be 16-byte aligned");
+    unsigned long long *key = (unsigned long long *)d_scratch;
+    int *cnt = (int *)((char *)d_scratch + align_up((int64_t)s->dev.mesh_count * scratch_rays * 8, 256));
+    trace_small_kernel<<<1, SMALL_THREADS, 0, (cudaStream_t)stream_>>>(
+        s->dev, (float4 *)d_org_pow, (float4 *)d_dir_prev, (unsigned long long *)d_lineage, (float4 *)d_dest_meas, (int4 *)d_hit,
+        arena_rays, n0, key, cnt, scratch_rays, (float4 *)d_measured_out, (unsigned long long *)d_measured_lineage,
+        d_measured_out ? measured_capacity : (1LL << 62), max_ray_len, ior_env, max_iterations, power_threshold, pair_limit,
+        (SmallIter *)d_iters, (SmallHeader *)d_header);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 #ifdef LPCL_TC_TRACE

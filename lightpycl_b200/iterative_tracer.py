@@ -498,19 +498,29 @@ class CL_Tracer:
             counters_host = self._counters_host
 
             gen = None
+            t_first, finished = 0, False
+            small = self._small_plan(n, int(trace_iterations))
             if n > 0:
-                org_pow = torch.empty((n, 4), dtype=torch.float32, device=self.device)
-                dir_prev = torch.empty((n, 4), dtype=torch.float32, device=self.device)
-                lineage = torch.empty(n, dtype=torch.int64, device=self.device) if self._lineage else None
+                cap0 = small["arena_rays"] if small else n
+                org_pow = torch.empty((cap0, 4), dtype=torch.float32, device=self.device)
+                dir_prev = torch.empty((cap0, 4), dtype=torch.float32, device=self.device)
+                lineage = torch.empty(cap0, dtype=torch.int64, device=self.device) if self._lineage else None
                 rc = lib.lpcl_pack_rays(job["origin"].data_ptr(), job["dir"].data_ptr(), job["power"].data_ptr(), None, n,
                                         job["lineage_base"], org_pow.data_ptr(), dir_prev.data_ptr(),
                                         lineage.data_ptr() if lineage is not None else None, self._stream())
                 _cabi.check(rc, "lpcl_pack_rays")
                 self.kernel_launches += 1
-                gen = _Generation(org_pow, dir_prev, lineage, n, n, n)
+                if small:
+                    # small scene: every generation in ONE launch (csrc/lpcl_small.cuh); the general loop below only
+                    # runs if the kernel hands a generation back (the rays multiplied beyond what one SM should trace)
+                    t_first, gen, finished = self._run_small(small, org_pow, dir_prev, lineage, n, int(trace_iterations),
+                                                             float(trace_until_dissipated), max_ray_len, ior_env, pow_shape,
+                                                             results, stream)
+                else:
+                    gen = _Generation(org_pow, dir_prev, lineage, n, n, n)
 
             epoch_start = 0  # iteration at which the current lineage numbering started (dist.renumber_lineage)
-            for t_iter in range(int(trace_iterations)):
+            for t_iter in range(t_first, 0 if finished else int(trace_iterations)):
                 n = gen.n if gen is not None else 0
                 if self.verbose:
                     print("ITERATION", t_iter + 1, "with ", n, "rays.")
@@ -605,9 +615,9 @@ class CL_Tracer:
                     break
             if prof:
                 stream.synchronize()
-                self.kernel_times = [dict(rays=n_, search_ms=sum(e[0].elapsed_time(e[1]) for e in ev_),
-                                          resolve_ms=sum(e[1].elapsed_time(e[2]) for e in ev_), tiles=len(ev_))
-                                     for n_, ev_ in events]
+                general = [dict(rays=n_, search_ms=sum(e[0].elapsed_time(e[1]) for e in ev_),
+                                resolve_ms=sum(e[1].elapsed_time(e[2]) for e in ev_), tiles=len(ev_)) for n_, ev_ in events]
+                self.kernel_times = (self.kernel_times if self.stats.get("one_launch_generations") else []) + general
         self.timings["run_s"] = time() - t_start
         return self.results
 
@@ -624,6 +634,92 @@ class CL_Tracer:
             if lin is not None:
                 lin[: self._measured_count] = self._measured_lineage[: self._measured_count]
         self._measured, self._measured_lineage = buf, lin
+
+    # ---------------------------------------------------------------------------------- small scenes
+    SMALL_PAIR_LIMIT = 1 << 16  # ray x triangle pairs per generation one CTA traces in ~10 us
+
+    def _small_plan(self, n, trace_iterations):
+        """Arena sizes for the one-launch trace of a small scene (csrc/lpcl_small.cuh), or None when the general
+        loop should run: several ranks (the termination tests are global), more than 8 meshes, a first generation
+        beyond SMALL_PAIR_LIMIT ray x triangle pairs, or LPCL_SMALL_PATH=0."""
+        tri = int(self.tri_count)
+        if (n <= 0 or trace_iterations < 1 or self.world_size > 1 or int(self.mesh_count) > 8
+                or n * tri > self.SMALL_PAIR_LIMIT or os.environ.get("LPCL_SMALL_PATH", "1") == "0"):
+            return None
+        per_gen = self.SMALL_PAIR_LIMIT // tri + 1                 # the largest generation the kernel accepts
+        iters = min(trace_iterations, 31)
+        return dict(scratch_rays=per_gen, iters=iters, arena_rays=min(n + 2 * iters * per_gen, 1 << 18))
+
+    def _run_small(self, plan, org_pow, dir_prev, lineage, n0, trace_iterations, trace_until_dissipated, max_ray_len, ior_env,
+                   pow_shape, results, stream):
+        """Launch the one-CTA trace, read its table back and turn it into the same state the general loop builds
+        (results, stats, measured buffer).  Returns (next iteration, generation to continue with, trace finished)."""
+        torch, lib = self._torch, self._lib
+        arena, iters = plan["arena_rays"], plan["iters"]
+        dest_meas = torch.empty((arena, 4), dtype=torch.float32, device=self.device)
+        hit = torch.empty((arena, 4), dtype=torch.int32, device=self.device) if self.record_hits else None
+        scratch = torch.empty(int(lib.lpcl_small_scratch_bytes(self._scene, plan["scratch_rays"])) + 256, dtype=torch.uint8,
+                              device=self.device)
+        table = torch.empty((iters + 1, 8), dtype=torch.int64, device=self.device)  # row 0: header, rows 1..: generations
+        self._reserve_measured(arena)
+        if getattr(self, "_small_host", None) is None or self._small_host.shape[0] < iters + 1:
+            self._small_host = torch.zeros((32, 8), dtype=torch.int64).pin_memory()
+        host = self._small_host[: iters + 1]
+        input_power = self._ensure_input_power()
+        threshold = (1.0 - trace_until_dissipated) * input_power
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if self.profile else None
+        if ev:
+            ev[0].record(stream)
+        rc = lib.lpcl_trace_small(
+            self._scene, org_pow.data_ptr(), dir_prev.data_ptr(), lineage.data_ptr() if lineage is not None else None,
+            dest_meas.data_ptr(), hit.data_ptr() if hit is not None else None, arena, n0, scratch.data_ptr(),
+            plan["scratch_rays"], self._measured.data_ptr(),
+            self._measured_lineage.data_ptr() if self._measured_lineage is not None else None, self._measured.shape[0],
+            C.c_float(max_ray_len), C.c_float(ior_env), iters, C.c_double(threshold), self.SMALL_PAIR_LIMIT,
+            table[1:].data_ptr(), table.data_ptr(), self._stream())
+        _cabi.check(rc, "lpcl_trace_small")
+        if ev:
+            ev[1].record(stream)
+        self.kernel_launches += 1
+        host.copy_(table, non_blocking=True)
+        stream.synchronize()
+        raw = host.numpy()
+        hdr = _cabi.SmallHeader.from_buffer_copy(raw[0].tobytes())
+        done = int(hdr.iterations)
+        split, base, cap = n0, n0, n0
+        tri = int(self.tri_count)
+        for k in range(done):
+            rec = _cabi.SmallIter.from_buffer_copy(raw[1 + k].tobytes())
+            n, off = int(rec.n_rays), int(rec.offset)
+            if self.keep_results:
+                gen = _Generation(org_pow[off: off + cap], dir_prev[off: off + cap],
+                                  lineage[off: off + cap] if lineage is not None else None, n, split, base)
+                results._append(gen, dest_meas[off: off + n], pow_shape if k == 0 else None)
+            else:
+                results.ray_counts.append(n)
+            if self.record_hits:
+                self.hit_records.append(hit[off: off + n])
+            live = int(rec.n_reflect + rec.n_refract)
+            for key, v in (("rays", n), ("live", live), ("live_local", live), ("power_left", float(rec.live_power)),
+                           ("candidates", n * tri), ("measured", int(rec.n_measured)), ("terminated", int(rec.n_terminated)),
+                           ("tiles", 1)):
+                self.stats[key].append(v)
+            self._measured_per_iter.append(int(rec.n_measured))
+            self._measured_count += int(rec.n_measured)
+            split, base, cap = int(rec.n_reflect), n, 2 * n
+            if self.verbose:
+                print("ITERATION", k + 1, "with ", n, "rays.")
+                print("Power left in scene:           ", rec.live_power / input_power * 100.0 if input_power else 0.0)
+        if ev:
+            self.kernel_times = [dict(rays=sum(self.stats["rays"]), search_ms=ev[0].elapsed_time(ev[1]), resolve_ms=0.0,
+                                      tiles=1, one_launch_trace=True)]
+        self.stats["one_launch_generations"] = done
+        if int(hdr.stop_reason) == 0:
+            return done, None, True
+        off, n = int(hdr.next_offset), int(hdr.next_n)
+        gen = _Generation(org_pow[off:], dir_prev[off:], lineage[off:] if lineage is not None else None, n,
+                          int(hdr.next_split), int(hdr.next_base))
+        return done, (gen if n > 0 else None), False
 
     def _tile_rays(self, n):
         """Rays per tile of a generation of n rays: as many as the scratch budget allows (12 B per

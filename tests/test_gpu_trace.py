@@ -308,3 +308,44 @@ def test_held_results_survive_later_traces():
         tr.iterative_tracer(ls2, meshes2, **params2)
         tr.get_measured_rays()
     assert np.array_equal(xyz, xyz_copy) and np.array_equal(pwr, pw_copy) and np.array_equal(geo0, geo_copy)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("c1_nested_cubes", dict(ray_count=10)),       # the reference example verbatim: 10 rays x 48 triangles
+    ("c1_nested_cubes", dict(ray_count=700)),      # grows past the one-CTA limit: handed over to the general loop
+    ("glass_cube_cavity", dict(ray_count=40, trace_iterations=40)),  # 31 generations in one launch, then the general loop
+    ("dissipative_cube", dict(ray_count=5)),
+])
+def test_one_launch_trace_of_small_scenes(name, kw, monkeypatch):
+    """Small scenes run every generation in ONE kernel launch (csrc/lpcl_small.cuh).  Bit-identical to the oracle,
+    to the general loop (LPCL_SMALL_PATH=0), and across the hand-over from one to the other."""
+    from lightpycl_b200 import iterative_tracer as it, scenes
+
+    ls, meshes, params = scenes.CONFIGS[name](**kw)
+    if name == "dissipative_cube":  # 10,378 triangles: only a handful of rays fit the pair limit
+        assert sum(s.ray_count for s in ls) * 10378 <= it.CL_Tracer.SMALL_PAIR_LIMIT
+    tr, ref = _check(name + " one launch", ls, meshes, params, lineage=True)
+    assert tr.stats.get("one_launch_generations", 0) >= 1
+    if name == "c1_nested_cubes" and kw["ray_count"] == 10:
+        assert tr.stats["one_launch_generations"] == len(tr.results) == 4 and tr.kernel_launches == 2
+    if kw.get("ray_count") == 700 or name == "glass_cube_cavity":
+        assert tr.stats["one_launch_generations"] < len(tr.results)  # the general loop finished the trace
+    monkeypatch.setenv("LPCL_SMALL_PATH", "0")
+    general = _trace_gpu(ls, meshes, params, lineage=True)
+    assert "one_launch_generations" not in general.stats
+    util.assert_results_equal(list(tr.results), list(general.results), name)
+    for a, b in zip(tr.hit_records, general.hit_records):
+        assert bool((a == b).all())
+    for (ga, _d, _p), (gb, _d2, _p2) in zip(tr.results._dev, general.results._dev):
+        assert bool((ga.logical(ga.lineage) == gb.logical(gb.lineage)).all())
+    for k in ("rays", "live", "measured", "terminated"):
+        assert tr.stats[k] == general.stats[k], k
+    pa, pb = tr.get_measured_rays(), general.get_measured_rays()
+    assert np.array_equal(util.bits(pa[0]), util.bits(pb[0]))
+    assert np.array_equal(util.bits(np.asarray(pa[1]).reshape(-1)), util.bits(np.asarray(pb[1]).reshape(-1)))
+    monkeypatch.delenv("LPCL_SMALL_PATH")
+    monkeypatch.setattr(it.CL_Tracer, "SMALL_PAIR_LIMIT", 48 * 12)  # hand over after the first generation(s)
+    if name == "c1_nested_cubes" and kw["ray_count"] == 10:
+        early = _trace_gpu(ls, meshes, params, lineage=True)
+        assert 1 <= early.stats["one_launch_generations"] < 4
+        util.assert_results_equal(list(early.results), list(general.results), name + " early hand-over")
