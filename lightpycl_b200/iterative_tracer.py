@@ -675,7 +675,7 @@ class CL_Tracer:
             dest_meas.data_ptr(), hit.data_ptr() if hit is not None else None, arena, n0, scratch.data_ptr(),
             plan["scratch_rays"], self._measured.data_ptr(),
             self._measured_lineage.data_ptr() if self._measured_lineage is not None else None, self._measured.shape[0],
-            C.c_float(max_ray_len), C.c_float(ior_env), iters, C.c_double(threshold), self.SMALL_PAIR_LIMIT,
+            C.c_float(max_ray_len), C.c_float(ior_env), trace_iterations, C.c_double(threshold), self.SMALL_PAIR_LIMIT,
             table[1:].data_ptr(), table.data_ptr(), self._stream())
         _cabi.check(rc, "lpcl_trace_small")
         if ev:

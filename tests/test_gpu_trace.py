@@ -313,22 +313,28 @@ def test_held_results_survive_later_traces():
 @pytest.mark.parametrize("name,kw", [
     ("c1_nested_cubes", dict(ray_count=10)),       # the reference example verbatim: 10 rays x 48 triangles
     ("c1_nested_cubes", dict(ray_count=700)),      # grows past the one-CTA limit: handed over to the general loop
-    ("glass_cube_cavity", dict(ray_count=40, trace_iterations=40)),  # 31 generations in one launch, then the general loop
+    ("glass_box_in_box", dict(ray_count=40, trace_iterations=40)),  # 31 generations in one launch, then the general loop
     ("dissipative_cube", dict(ray_count=5)),
 ])
 def test_one_launch_trace_of_small_scenes(name, kw, monkeypatch):
     """Small scenes run every generation in ONE kernel launch (csrc/lpcl_small.cuh).  Bit-identical to the oracle,
     to the general loop (LPCL_SMALL_PATH=0), and across the hand-over from one to the other."""
-    from lightpycl_b200 import iterative_tracer as it, scenes
+    from lightpycl_b200 import geo_optical_elements as goe, iterative_tracer as it, scenes
 
-    ls, meshes, params = scenes.CONFIGS[name](**kw)
+    if name == "glass_box_in_box":  # glass_cube_cavity with a 12-triangle measure box instead of the 10,366-triangle sphere
+        ls, meshes, params = scenes.glass_cube_cavity(**kw)
+        box = goe.optical_elements().cube(center=(0, 0, 0, 0), size=[200, 200, 200, 0])
+        box.setMaterial(mat_type="measure")
+        meshes = [box, meshes[1]]
+    else:
+        ls, meshes, params = scenes.CONFIGS[name](**kw)
     if name == "dissipative_cube":  # 10,378 triangles: only a handful of rays fit the pair limit
         assert sum(s.ray_count for s in ls) * 10378 <= it.CL_Tracer.SMALL_PAIR_LIMIT
     tr, ref = _check(name + " one launch", ls, meshes, params, lineage=True)
     assert tr.stats.get("one_launch_generations", 0) >= 1
     if name == "c1_nested_cubes" and kw["ray_count"] == 10:
         assert tr.stats["one_launch_generations"] == len(tr.results) == 4 and tr.kernel_launches == 2
-    if kw.get("ray_count") == 700 or name == "glass_cube_cavity":
+    if kw.get("ray_count") == 700 or name == "glass_box_in_box":
         assert tr.stats["one_launch_generations"] < len(tr.results)  # the general loop finished the trace
     monkeypatch.setenv("LPCL_SMALL_PATH", "0")
     general = _trace_gpu(ls, meshes, params, lineage=True)
