@@ -146,31 +146,34 @@ def merge_measured(records, lineages, iter_ids):
 def gather_measured(pos_pwr, lineage, per_iter, group, device):
     """All ranks receive every rank's measured records, merged into the reference order.
 
-    pos_pwr (K,4) f32, lineage (K,) i64, per_iter: this rank's measured count per iteration."""
+    pos_pwr (K,4) f32, lineage (K,) i64, per_iter: this rank's measured count per iteration (every rank ran the
+    same number of iterations: the termination tests are global).  Two padded all-gathers (records, lineage) and
+    one small one (the per-iteration counts, from which every rank rebuilds the iteration of each record)."""
     td = _td()
     ws, _ = world(group)
     dev = _comm_device(group, device)
     k = int(pos_pwr.shape[0])
-    iters = torch.repeat_interleave(torch.arange(len(per_iter), dtype=torch.int64),
-                                    torch.tensor(per_iter, dtype=torch.int64)) if len(per_iter) else \
-        torch.zeros(0, dtype=torch.int64)
-    counts = all_gather_int(k, group, device)
+    n_iter = len(per_iter)
+    mine = torch.tensor(list(per_iter) + [k], dtype=torch.int64, device=dev)  # per-iteration counts, then the total
+    table = [torch.empty_like(mine) for _ in range(ws)]
+    td.all_gather(table, mine, group=_pg(group))
+    table = torch.stack(table).cpu()
+    counts = [int(c) for c in table[:, n_iter]]
     kmax = max(max(counts), 1)
     rec = torch.zeros((kmax, 4), dtype=torch.float32, device=dev)
     lin = torch.zeros(kmax, dtype=torch.int64, device=dev)
-    itr = torch.zeros(kmax, dtype=torch.int64, device=dev)
     if k:
         rec[:k] = pos_pwr.to(dev)
         lin[:k] = lineage.to(dev)
-        itr[:k] = iters.to(dev)
-    recs = [torch.zeros_like(rec) for _ in range(ws)]
-    lins = [torch.zeros_like(lin) for _ in range(ws)]
-    itrs = [torch.zeros_like(itr) for _ in range(ws)]
+    recs = [torch.empty_like(rec) for _ in range(ws)]
+    lins = [torch.empty_like(lin) for _ in range(ws)]
     td.all_gather(recs, rec, group=_pg(group))
     td.all_gather(lins, lin, group=_pg(group))
-    td.all_gather(itrs, itr, group=_pg(group))
     rec_all = torch.cat([r[:c] for r, c in zip(recs, counts)], dim=0)
     lin_all = torch.cat([r[:c] for r, c in zip(lins, counts)], dim=0)
-    itr_all = torch.cat([r[:c] for r, c in zip(itrs, counts)], dim=0)
-    merged, _, _ = merge_measured(rec_all, lin_all, itr_all)
-    return merged
+    # records are iteration-major inside a rank: rank r contributes table[r, i] records of iteration i, in that order
+    iters = torch.arange(n_iter, dtype=torch.int64).repeat(ws)
+    itr_all = torch.repeat_interleave(iters, table[:, :n_iter].reshape(-1)).to(dev)
+    order = torch.sort(lin_all, stable=True).indices
+    order = order[torch.sort(itr_all[order], stable=True).indices]
+    return rec_all[order]
