@@ -368,7 +368,11 @@ class CL_Tracer:
         self._lineage = bool(lineage) if lineage is not None else self.world_size > 1
         self.ray_tile_bytes = int(ray_tile_bytes if ray_tile_bytes is not None
                                   else os.environ.get("LPCL_RAY_TILE_BYTES", 8 << 30))
-        self._host_pool = _HostPool(pinned=True)
+        # LPCL_PIN_HOST=1: page-locked host staging (the result / geometry pool, and source arrays met twice).  Off by
+        # default: page-locking costs 1-2 ms per MB ONCE (measured: 45 ms to register 36 MB of rays, 35 ms to allocate
+        # an 18 MB result buffer), which only a loop of many traces over the same sources earns back (4 ms per trace)
+        self._pin_host = os.environ.get("LPCL_PIN_HOST", "0") == "1"
+        self._host_pool = _HostPool(pinned=self._pin_host)
         self.shard_input = shard_input
         self.profile = profile
         self.kernel_times = []
@@ -499,13 +503,13 @@ class CL_Tracer:
     PAGE_LOCK_BUDGET = 1 << 30  # bytes of caller memory this tracer keeps registered at most
 
     def _page_lock_if_seen_again(self, arr):
-        """Uploading rays from pageable memory runs at ~1/4 of the DMA rate (4.1 vs 0.9 ms per 1M rays).  The light
-        sources stay plain NumPy; instead, when prepare() meets the SAME source array a second time (a
-        sweep over geometries, a benchmark loop) the tracer page-locks that memory in place (cudaHostRegister, on its
-        own device) so that later uploads are direct DMA.  The registration is undone when the array's owner is
+        """Opt-in (LPCL_PIN_HOST=1).  Uploading rays from pageable memory runs at ~1/4 of the DMA rate (4.1 vs 0.9 ms per
+        1M rays).  The light sources stay plain NumPy; instead, when prepare() meets the SAME source array a
+        second time (a sweep over geometries, a loop of traces) the tracer page-locks that memory in place
+        (cudaHostRegister, on its own device) so that later uploads are direct DMA.  The registration is undone when the array's owner is
         garbage collected; at most PAGE_LOCK_BUDGET bytes are registered; a refusal by the driver just leaves the
         array pageable."""
-        if arr.nbytes < (1 << 20):
+        if not self._pin_host or arr.nbytes < (1 << 20):
             return
         state = self.__dict__.setdefault("_page_locks", dict(seen={}, locked={}, bytes=0))
         key = (arr.ctypes.data, arr.nbytes)
