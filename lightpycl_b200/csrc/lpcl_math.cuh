@@ -167,26 +167,25 @@ LPCL_HD float filter_ray_scale(V3 o, V3 d, float vmax)
     float f = L / (4.0f * vmax);
     return 1.2e-7f * d2 * L * (f > 1.0f ? f : 1.0f); // 2 * 2^-24 = 1.19e-7
 }
-// The same K2 with V = a bound of the vertex norms of ONE TILE of triangles (the derivation only
-// needs |V0| + Emax <= 2 V for the triangle at hand): the ray keeps |O| and 2 u |D|^2, the tile brings
-// 2 V and 1 / (4 V).  Used by the tensor-core search, whose tiles store their own bound - a scene
-// with a large far shell (a measure dome) no longer inflates the margin of its small inner triangles.
+// Ray part of the tensor-core filter's margin (derivation below, "the same filter evaluated by the
+// tensor cores"): k = 268 u |D| L with L = |O| + 2 V, V = a bound of the vertex norms of ONE TILE of
+// triangles (the derivation only needs |V0| + Emax <= 2 V for the triangle at hand).  The ray keeps |O|
+// and 268 u |D|, the tile brings 2 V: one multiply-add when V changes.  A scene with a large far shell
+// (a measure dome) does not inflate the margin of its small inner triangles.
 struct RayScale {
-    float lo;   // |O|
-    float d2u;  // 1.2e-7 |D|^2
+    float lo;  // |O|
+    float du;  // 1.6e-5 |D|    (268 * 2^-24 = 1.597e-5)
 };
 LPCL_HD RayScale filter_ray_parts(V3 o, V3 d)
 {
     RayScale r;
     r.lo = sqrtf(o.x * o.x + o.y * o.y + o.z * o.z);
-    r.d2u = 1.2e-7f * (d.x * d.x + d.y * d.y + d.z * d.z);
+    r.du = 1.6e-5f * sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
     return r;
 }
-LPCL_HD float filter_ray_scale_tile(RayScale r, float two_v, float inv_four_v)
+LPCL_HD float filter_ray_scale_tile(RayScale r, float two_v)
 {
-    float L = r.lo + two_v;
-    float f = L * inv_four_v;
-    return r.d2u * L * (f > 1.0f ? f : 1.0f);
+    return r.du * (r.lo + two_v);
 }
 
 // The filter for one (ray, triangle), operation by operation as the packed device loop evaluates
@@ -224,14 +223,17 @@ LPCL_HD bool filter_candidate(const FilterRec &q, float dx, float dy, float dz, 
 // hi.hi + hi.lo + lo.hi + lo.lo are laid along K (4 x 6 = 24 = three kind::tf32 MMAs of K = 8).
 //
 // The three rows per triangle are DEN, aU = 2 uN - DEN and aV = 2 vN - DEN (still linear in the
-// ray), because  uN (DEN - uN) = (DEN^2 - aU^2) / 4 :  the two product tests become
-//   DEN^2 + m - aU^2 >= 0   and   DEN^2 + m - aV^2 >= 0,
-// three multiply-adds per triangle - d2 = fma(DEN, DEN, m), fma(-aU, aU, d2), fma(-aV, aV, d2) -
-// instead of two subtractions and two multiply-adds: the CUDA-core epilogue, not the tensor pipe,
-// bounds the kernel, so an instruction per pair of triangles less is 10 % of the sweep.
-// Each triangle's three rows are pre-scaled by s = 1/sqrt(G2tc_tri), which turns the margin
-// m = K2_ray * G2tc_tri into the per-RAY constant K2_ray:
-//   candidate  <=>  DEN'^2 + K2_ray - aU'^2 >= 0  and  DEN'^2 + K2_ray - aV'^2 >= 0.
+// ray).  The reference accepts only if 0 <= uN/DEN <= 1 and 0 <= vN/DEN <= 1, i.e. only if
+// |aU| <= |DEN| and |aV| <= |DEN| whatever the sign of DEN (the parallelogram spanned by the triangle), so
+//   candidate  <=>  |DEN| - max(|aU|, |aV|) + k >= 0          (the LINEAR form)
+// - per triangle one FMNMX and one FADD (absolute values are SASS operand modifiers), and the chunk-wide
+// "any candidate?" is a running maximum, one three-input FMNMX3 per PAIR of triangles: 2.5 issue slots
+// per test instead of the 4 of the square form DEN^2 + m - aU^2 >= 0 (three packed multiply-adds and two
+// LOP3 per pair, a packed instruction holding the issue port for two cycles), which this kernel used
+// before: the CUDA-core epilogue, not the tensor pipe, bounds the kernel.  Every maximum propagates NaN
+// (max.NaN), and a NaN passes the final comparison: overflowing inputs become candidates, never misses.
+// Each triangle's three rows are pre-scaled by s = 1 / Emax_tri, which turns the margin
+// k = 268 u |D| L Emax_tri into the per-RAY constant k_ray = 268 u |D| L.
 //
 // Margin.  Measured on B200 (tools/ubench_tmem.cu, profiles/r1_ubench_tmem.txt): a kind::tf32
 // tcgen05.mma sums its K = 8 products and the accumulator with extra bits and truncates once
@@ -240,15 +242,13 @@ LPCL_HD bool filter_candidate(const FilterRec &q, float dx, float dy, float dz, 
 // rounding <= 1 u: eps_filter <= (16 + 6 + 5) u |D| Emax (|O| + |V0|), plus the reference's own
 // 7 u, times the same 1.5 allowance: eps = 56 u |D| Emax L bounds |DEN_f - DEN_ref|; the aU / aV
 // rows carry three times the terms, 3 eps.  If the reference accepts, uN_ref and DEN_ref have equal
-// signs and |uN_ref| <= |DEN_ref| (1 + 3u), i.e. |aU_ref| <= |d| (1 + 6u) with d = DEN_ref,
-// |d| <= |D| E12; then
-//   aU_f^2 - DEN_f^2 <= 13 u d^2 + 2 |d| (3 eps + eps)(1 + 6u) + (4 eps)^2,
-// and the two roundings of the epilogue's multiply-adds add <= u DEN_f^2: the test passes whenever
-//   m >= u |D|^2 Emax L (463 E12 + 50176 u Emax L)        (E12^2 <= E12 Emax L was used),
-// which the separable product of K2_ray (above, unchanged) and
-//   G2tc_tri = Emax (463 E12 + 50176 u Emax Lcap)
-// covers with a factor 2 to spare.  (The product form uN (DEN - uN) of the fp32 filter needs
-// 4 x (172 E12 + 6272 u Emax L) in these units: the square form is no wider.)
+// signs and |uN_ref| <= |DEN_ref| (1 + 3u), i.e. |aU_ref| <= |d| (1 + 6u) with d = DEN_ref; then
+//   |aU_f| <= |aU_ref| + 3 eps <= (|DEN_f| + eps)(1 + 6u) + 3 eps,
+//   |aU_f| - |DEN_f| <= 6u |DEN_f| + (4 + 6u) eps <= (6 + 224 + 1) u |D| Emax L = 231 u |D| Emax L
+// (|DEN_f| <= |D| E12 + eps and E12 <= Emax . 2V <= Emax L were used), and the same for aV.  The epilogue's own
+// subtraction and the addition of k round by <= u relative each.  k = 268 u |D| Emax L covers that with 16 % to
+// spare.  In the units of the square form (aU^2 - DEN^2 <= m means |aU| - |DEN| <= m / (|aU| + |DEN|) ~ 463 .. 926 u
+// |D| Emax L / cos(incidence)) the linear margin is 2 - 4 x narrower: fewer false candidates as well.
 LPCL_HD float tf32_rna(float x) // round to nearest (ties away) to 10 explicit mantissa bits, as cvt.rna.tf32.f32
 {
     union { float f; uint32_t u; } v;
@@ -273,8 +273,7 @@ LPCL_HD TcRows make_tc_rows(V3 v0, V3 v1, V3 v2, float vmax)
     double ox = v0.x, oy = v0.y, oz = v0.z;
     double l1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z), l2 = sqrt(e2x * e2x + e2y * e2y + e2z * e2z);
     double emax = l1 > l2 ? l1 : l2;
-    double g = emax * (463.0 * l1 * l2 + 2.991e-3 * emax * 4.0 * (double)vmax) * 1.001; // 50176 * 2^-24 = 2.9907e-3
-    double s = 1.0 / sqrt(g > 1e-30 ? g : 1e-30);
+    double s = 1.0 / (emax > 1e-30 ? emax : 1e-30); // rows in units of Emax: the margin becomes a per-ray constant
     const double nn[3] = {e2y * e1z - e2z * e1y, e2z * e1x - e2x * e1z, e2x * e1y - e2y * e1x}; // Nn = E2 x E1
     const double a[3] = {oy * e2z - oz * e2y, oz * e2x - ox * e2z, ox * e2y - oy * e2x};         // A = V0 x E2
     const double b[3] = {e1y * oz - e1z * oy, e1z * ox - e1x * oz, e1x * oy - e1y * ox};         // B = E1 x V0
@@ -294,9 +293,9 @@ LPCL_HD TcRows make_tc_rows(V3 v0, V3 v1, V3 v2, float vmax)
 // Host model of the tensor-core filter for the property test: the three GEMM outputs are formed
 // exactly from the split operands (double), then pushed by +-16 u sum|terms| in the direction
 // `push` selects (bit 0: DEN', bit 1: aU', bit 2: aV'); the caller requires a reference hit to be a
-// candidate for every push.  The epilogue's three multiply-adds are evaluated as the GPU does.
+// candidate for every push.  The epilogue's maximum, subtraction and addition are evaluated as the GPU does.
 // Not used on the GPU.
-LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, float mx, float my, float mz, float k2, int push)
+LPCL_HD float filter_value_tc(const TcRows &q, float dx, float dy, float dz, float mx, float my, float mz, int push)
 {
     const float a[6] = {mx, my, mz, dx, dy, dz};
     float out[3];
@@ -313,10 +312,11 @@ LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, 
         const double e = 16.0 * 5.9604644775390625e-8 * sabs;
         out[r] = (float)(s + (((push >> r) & 1) ? e : -e));
     }
-    const float d2 = LPCL_FMA(out[0], out[0], k2);
-    const float pu = LPCL_FMA(-out[1], out[1], d2);
-    const float pv = LPCL_FMA(-out[2], out[2], d2);
-    return !(signbit(pu) || signbit(pv));
+    return fabsf(out[0]) - fmaxf(fabsf(out[1]), fabsf(out[2]));
+}
+LPCL_HD bool filter_candidate_tc(const TcRows &q, float dx, float dy, float dz, float mx, float my, float mz, float kray, int push)
+{
+    return !(filter_value_tc(q, dx, dy, dz, mx, my, mz, push) + kray < 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------

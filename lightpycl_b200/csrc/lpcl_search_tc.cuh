@@ -190,6 +190,20 @@ __device__ __forceinline__ void tc_ld_48(uint32_t taddr, uint32_t *r)
                  : "memory");
 }
 
+// maxima that propagate NaN (an overflowed filter value must become a candidate, never a silent miss)
+__device__ __forceinline__ float fmax_nan(float a, float b)
+{
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) // FMNMX3 (sm_100+)
+{
+    float d;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------------------------------ exact path
 // Candidates are not evaluated where they are found: a lane that finds some appends (ray, triangle,
 // mesh) records to its warp's queue in shared memory and the sweep goes on.  When the queue is
@@ -330,7 +344,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     const int half = (warp >> 2) & 1;
     const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
     const ExactLimits eps = {eps_len(max_ray_len), max_ray_len};
-    RayScale rs[RT]; // |O| and 2 u |D|^2 of this thread's ray in each ray tile: the margin constant K2 is rebuilt per triangle tile
+    RayScale rs[RT]; // |O| and 268 u |D| of this thread's ray in each ray tile: the margin constant k is rebuilt when the tile bound Vc changes
     if (warp < TC_EPI_WARPS) {
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
@@ -416,37 +430,28 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
         const int steps = nt * RT;
         uint32_t rA[48], rB[48];
 
-        // the two tests on 16 triangles x this lane's ray in the square form (lpcl_math.cuh):
-        //   d2 = DEN'^2 + K2,  du = d2 - aU'^2,  dv = d2 - aV'^2   (three FFMA2 per PAIR of triangles; the
-        // negations are operand modifiers); a negative du or dv = not a candidate.  Candidates go to the warp's queue
-        auto test_chunk = [&](const uint32_t(&r)[48], float2 kk, int first, int tri0, int count, int mesh, long long i) {
-            float2 du[8], dv[8];
-            unsigned none[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}; // a sign bit survives only if every test failed
+        // the test on 16 triangles x this lane's ray in the linear form (lpcl_math.cuh): per triangle
+        //   f = |DEN'| - max(|aU'|, |aV'|)        (FMNMX + FADD, absolute values are operand modifiers)
+        // and the chunk's largest f through a three-input FMNMX3 per PAIR of triangles (two independent chains);
+        // f + k < 0 = not a candidate.  Every maximum propagates NaN and a NaN passes.  Candidates go to the warp's queue
+        auto test_chunk = [&](const uint32_t(&r)[48], float kk, int first, int tri0, int count, int mesh, long long i) {
+            float top[2] = {-3.0e38f, -3.0e38f};
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float2 den = make_float2(__uint_as_float(r[6 * q + 0]), __uint_as_float(r[6 * q + 1]));
-                const float2 au = make_float2(__uint_as_float(r[6 * q + 2]), __uint_as_float(r[6 * q + 3]));
-                const float2 av = make_float2(__uint_as_float(r[6 * q + 4]), __uint_as_float(r[6 * q + 5]));
-                const float2 d2 = __ffma2_rn(den, den, kk);
-                du[q] = __ffma2_rn(make_float2(-au.x, -au.y), au, d2);
-                dv[q] = __ffma2_rn(make_float2(-av.x, -av.y), av, d2);
-                none[(2 * q) & 3] = or_and(__float_as_uint(du[q].x), __float_as_uint(dv[q].x), none[(2 * q) & 3]);
-                none[(2 * q + 1) & 3] = or_and(__float_as_uint(du[q].y), __float_as_uint(dv[q].y), none[(2 * q + 1) & 3]);
+                const float fa = fabsf(__uint_as_float(r[6 * q + 0])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 2])), fabsf(__uint_as_float(r[6 * q + 4])));
+                const float fb = fabsf(__uint_as_float(r[6 * q + 1])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 3])), fabsf(__uint_as_float(r[6 * q + 5])));
+                top[q & 1] = fmax3_nan(top[q & 1], fa, fb);
             }
-            const bool some = (int)(none[0] & none[1] & none[2] & none[3]) >= 0; // rare: a triangle of the chunk passed both tests
+            const bool some = !(fmax_nan(top[0], top[1]) + kk < 0.0f); // rare: a triangle of the chunk passed
             if (__any_sync(0xffffffffu, some)) { // warp-uniform branch: the common path carries no reconvergence code
                 if (some) {
-                    // sign bits (1 = failed) funnel-shifted in from the top triangle down, as two independent chains:
-                    // bit t of f_lo = triangle t, bit t of f_hi = triangle 8 + t
-                    unsigned f_lo = 0, f_hi = 0;
+                    unsigned mask = 0; // bit t = triangle `first + t` passed
 #pragma unroll
-                    for (int q = 3; q >= 0; --q) {
-                        f_lo = __funnelshift_l(__float_as_uint(du[q].y) | __float_as_uint(dv[q].y), f_lo, 1);
-                        f_hi = __funnelshift_l(__float_as_uint(du[q + 4].y) | __float_as_uint(dv[q + 4].y), f_hi, 1);
-                        f_lo = __funnelshift_l(__float_as_uint(du[q].x) | __float_as_uint(dv[q].x), f_lo, 1);
-                        f_hi = __funnelshift_l(__float_as_uint(du[q + 4].x) | __float_as_uint(dv[q + 4].x), f_hi, 1);
+                    for (int t = 0; t < TC_CHUNK_TRIS; ++t) {
+                        const int c = 6 * (t >> 1) + (t & 1);
+                        const float f = fabsf(__uint_as_float(r[c])) - fmax_nan(fabsf(__uint_as_float(r[c + 2])), fabsf(__uint_as_float(r[c + 4])));
+                        if (!(f + kk < 0.0f)) mask |= 1u << t;
                     }
-                    unsigned mask = ~((f_lo & 0xffu) | (f_hi << 8)) & 0xffffu;
                     const int valid = count - first; // padded triangle slots of a mesh's last tile are not candidates
                     if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
                     n_cand += __popc(mask);
@@ -463,7 +468,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             tc_ld_48(lane_addr + 48u, rB);
         }
         int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
-        float2 k2s[RT];
+        float k2s[RT];
         int vc_bits = 0; // Vc is a positive float: the first tile always differs
         for (int it = 0; it < nt; ++it) {
             const int4 ti4 = ti_next; // fetched one tile ahead: the L2 latency is off the critical path
@@ -471,17 +476,14 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
             if (ti4.w != vc_bits) { // K2 of (this thread's ray in each ray tile, tiles with this Vc): rebuilt when Vc changes
                 vc_bits = ti4.w;
-                const float two_vc = 2.0f * __int_as_float(vc_bits), inv_four_vc = __frcp_rn(4.0f * __int_as_float(vc_bits));
+                const float two_vc = 2.0f * __int_as_float(vc_bits);
 #pragma unroll
-                for (int j = 0; j < RT; ++j) {
-                    const float kk = filter_ray_scale_tile(rs[j], two_vc, inv_four_vc);
-                    k2s[j] = make_float2(kk, kk);
-                }
+                for (int j = 0; j < RT; ++j) k2s[j] = filter_ray_scale_tile(rs[j], two_vc);
             }
 #pragma unroll
             for (int j = 0; j < RT; ++j) {
                 const int g = it * RT + j, buf = g & 1;
-                const float2 k2 = k2s[j];
+                const float k2 = k2s[j];
                 const bool more = g + 1 < steps;
                 const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
                 const long long i = ray0 + (long long)j * TC_M;

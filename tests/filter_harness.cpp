@@ -55,10 +55,14 @@ static long property(int tc, long n, unsigned seed, double scene_radius, double 
             // the tile-local vertex-norm bound: anything from this triangle's own largest vertex norm upwards
             float na = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), nb = sqrtf(b.x * b.x + b.y * b.y + b.z * b.z), nc = sqrtf(c.x * c.x + c.y * c.y + c.z * c.z);
             float vloc = fmaxf(fmaxf(na, nb), fmaxf(nc, 1e-30f)) * 1.0001f * (float)(1.0 + (rnd() < 0.5 ? 0.0 : 3.0 * rnd()));
-            k2 = filter_ray_scale_tile(filter_ray_parts(o, d), 2.0f * vloc, 1.0f / (4.0f * vloc));
+            k2 = filter_ray_scale_tile(filter_ray_parts(o, d), 2.0f * vloc);
             TcRows q = make_tc_rows(a, b, c, vloc);
             cand = true;
-            for (int push = 0; push < 8; ++push) cand = cand && filter_candidate_tc(q, d.x, d.y, d.z, mx, my, mz, k2, push);
+            for (int push = 0; push < 8; ++push) {
+                cand = cand && filter_candidate_tc(q, d.x, d.y, d.z, mx, my, mz, k2, push);
+                // the share of the margin a reference hit actually needed (1 = the filter would have dropped it)
+                if (hit) *worst = fmax(*worst, -(double)filter_value_tc(q, d.x, d.y, d.z, mx, my, mz, push) / (double)k2);
+            }
         } else {
             FilterRec q = make_filter_rec(a, b, c, vmax);
             cand = filter_candidate(q, d.x, d.y, d.z, mx, my, mz, k2);
