@@ -57,6 +57,8 @@ struct TcVariant {
 static const TcVariant kTcVariants[] = {
     {1, search_tc_kernel<1>}, {2, search_tc_kernel<2>}, {4, search_tc_kernel<4>}, {8, search_tc_kernel<8>}};
 static const int kNumTcVariants = (int)(sizeof(kTcVariants) / sizeof(kTcVariants[0]));
+static const TcVariant kTc16Variants[] = { // LPCL_TC_WARPS=16: two groups of eight thin epilogue warps (RT even; RT = 1 uses the default kernel)
+    {1, nullptr}, {2, search_tc16_kernel<2>}, {4, search_tc16_kernel<4>}, {8, search_tc16_kernel<8>}};
 
 struct lpcl_scene {
     SceneDev dev;
@@ -220,9 +222,13 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     build_tc_kernel<<<(unsigned)((tc_slots + 127) / 128), 128, 0, stream>>>(d.v0, d.v1, d.v2, d.tc_tiles, tc_n_tiles,
                                                                            (float *)(base + off_tc_filter));
     SCENE_TRY(cudaGetLastError());
-    for (int v = 0; v < kNumTcVariants; ++v)
+    for (int v = 0; v < kNumTcVariants; ++v) {
         SCENE_TRY(cudaFuncSetAttribute(kTcVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        tc_smem_bytes(kTcVariants[v].rt)));
+        if (kTc16Variants[v].fn)
+            SCENE_TRY(cudaFuncSetAttribute(kTc16Variants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tc16_smem_bytes(kTc16Variants[v].rt)));
+    }
     for (int v = 0; v < kNumVariants; ++v) {
         SCENE_TRY(cudaFuncSetAttribute(kVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_SMEM_BYTES));
         int occ = 0;
@@ -351,8 +357,12 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         int tiles_per_chunk = (int)((s->dev.tc_n_tiles + chunks - 1) / chunks);
         chunks = (s->dev.tc_n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
         dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
-        kTcVariants[v].fn<<<grid, TC_THREADS, tc_smem_bytes(kTcVariants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
-                                                                                          tiles_per_chunk, cand_total);
+        if (env_int("LPCL_TC_WARPS", 8) == 16 && kTc16Variants[v].fn)
+            kTc16Variants[v].fn<<<grid, TC16_THREADS, tc16_smem_bytes(kTc16Variants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
+                                                                                                      tiles_per_chunk, cand_total);
+        else
+            kTcVariants[v].fn<<<grid, TC_THREADS, tc_smem_bytes(kTcVariants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
+                                                                                              tiles_per_chunk, cand_total);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

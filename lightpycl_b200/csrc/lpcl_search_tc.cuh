@@ -523,4 +523,253 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
     if (warp == TC_MMA_WARP) tc_free_512(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------ thin-warp variant
+// LPCL_TC_WARPS=16: sixteen epilogue warps (four per SM sub-partition, 96-register cap) in TWO GROUPS of eight.  Group h
+// owns accumulator h, i.e. every other (ray tile, triangle tile) step; inside a group warp w reads TMEM lanes 32 (w % 4)..
+// and tests the two 16-triangle chunks of half (w / 4) % 2 one after the other through a single 48-register buffer
+// (load, wait, test, load, wait, release, test - nothing is software pipelined inside a warp; the other group, half a
+// period away, fills the gaps).  Same filter arithmetic, queues and exact path as search_tc_kernel, bit-identical
+// results.  Measured (profiles/r2b_kbench_variants.log): C3 4.14e12 vs 4.19e12 tests/s for the default kernel, C2 3.34e12
+// vs 2.96e12 (+13 %: a sixth of C2's chunk tests take the candidate branch, which stalls a fat warp's whole pipeline),
+// C4 2.96e12 vs 2.91e12.  Selectable, not the default (the headline workload is C3).
+constexpr int TC16_EPI_WARPS = 16;
+constexpr int TC16_PRODUCER_WARP = 16;
+constexpr int TC16_MMA_WARP = 17;
+constexpr int TC16_THREADS = 576;
+constexpr int TC16_QUEUE_CAP = 128;
+constexpr int TC16_QUEUE_DRAIN = 64;
+
+__host__ __device__ constexpr int tc16_smem_bytes(int rt)
+{
+    return (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + TC16_EPI_WARPS * (TC16_QUEUE_CAP * 16 + 16) + 256) > 120 * 1024
+               ? (TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + TC16_EPI_WARPS * (TC16_QUEUE_CAP * 16 + 16) + 256)
+               : 120 * 1024;
+}
+
+__device__ __noinline__ void tc16_drain(int4 *queue, int *q_count, const SceneDev &sc, const RaysDev &rays, ExactLimits eps,
+                                        unsigned long long *key, int *cnt)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int total = min(*q_count, TC16_QUEUE_CAP);
+    for (int k = lane; k < total; k += 32) {
+        const int4 e = queue[k];
+        if (e.y >= 0) {
+            queue[k].y = -1;
+            tc_exact_one(sc, rays, (long long)(unsigned)e.x, e.y, e.z, eps, key, cnt);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *q_count = 0;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void tc16_enqueue(unsigned mask, int tri_base, long long i, int mesh, int4 *queue, int *q_count,
+                                             const SceneDev &sc, const RaysDev &rays, ExactLimits eps, unsigned long long *key, int *cnt)
+{
+    const int c = __popc(mask);
+    const int pos = atomicAdd(q_count, c);
+    if (pos + c <= TC16_QUEUE_CAP) {
+        int k = pos;
+        while (mask) {
+            const int b = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            queue[k++] = make_int4((int)i, tri_base + b, mesh, 0);
+        }
+    } else {
+        tc_overflow(mask, tri_base, i, mesh, sc, rays, eps, key, cnt);
+    }
+}
+
+template <int RT>
+__global__ void __launch_bounds__(TC16_THREADS, 1)
+search_tc16_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *__restrict__ key, int *__restrict__ cnt,
+                   int tiles_per_chunk, unsigned long long *cand_total)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *b_buf = reinterpret_cast<float *>(smem_raw);
+    float *a_buf = reinterpret_cast<float *>(smem_raw + TC_STAGES * TC_TILE_BYTES);
+    int4 *queues = reinterpret_cast<int4 *>(smem_raw + TC_STAGES * TC_TILE_BYTES + RT * TC_A_BYTES);
+    int *q_counts = reinterpret_cast<int *>(queues + TC16_EPI_WARPS * TC16_QUEUE_CAP); // one per 16 bytes
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(q_counts + TC16_EPI_WARPS * 4);
+    uint64_t *empty_bar = full_bar + TC_STAGES;
+    uint64_t *tfull_bar = empty_bar + TC_STAGES;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int c0 = blockIdx.y * tiles_per_chunk;
+    const int c1 = min(c0 + tiles_per_chunk, sc.tc_n_tiles);
+    const int nt = max(c1 - c0, 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], TC16_EPI_WARPS / 2); // only the accumulator's own group of warps releases it
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC16_MMA_WARP) tc_alloc_512(tmem_slot);
+
+    const int row = (warp & 3) * 32 + lane; // TMEM lane == ray row of every ray tile
+    const int chunk = (warp >> 2) & 3;      // (A staging only) which of the four threads of a row stages it
+    const int group = (warp >> 3) & 1;      // the group owns accumulator `group`, i.e. the steps g = group (mod 2)
+    const int sub = (warp >> 2) & 1;        // this warp tests chunks 2 sub and 2 sub + 1 of its group's steps
+    const long long ray0 = (long long)blockIdx.x * (RT * TC_M) + row;
+    const ExactLimits eps = {eps_len(max_ray_len), max_ray_len};
+    if (warp < TC16_EPI_WARPS) {
+#pragma unroll
+        for (int j = 0; j < RT; ++j) {
+            if ((j & 3) == chunk) { // each ray row of each ray tile is staged by one of its four threads
+                const long long i = min(ray0 + (long long)j * TC_M, rays.n - 1);
+                const long long ph = rays.phys(i);
+                const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
+                const float a6[6] = {o.y * d.z - o.z * d.y, o.z * d.x - o.x * d.z, o.x * d.y - o.y * d.x, d.x, d.y, d.z};
+                float *dst = a_buf + j * TC_A_FLOATS;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    float hi, lo;
+                    tf32_split(a6[k], hi, lo);
+                    dst[tc_canon(row, k, TC_M)] = hi;
+                    dst[tc_canon(row, 6 + k, TC_M)] = hi;
+                    dst[tc_canon(row, 12 + k, TC_M)] = lo;
+                    dst[tc_canon(row, 18 + k, TC_M)] = lo;
+                }
+            }
+        }
+        for (int k = lane; k < TC16_QUEUE_CAP; k += 32) queues[warp * TC16_QUEUE_CAP + k] = make_int4(0, -1, 0, 0);
+        if (lane == 0) q_counts[warp * 4] = 0;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TC16_PRODUCER_WARP) {
+        for (int it = 0; it < nt; ++it) {
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (unsigned)((it / TC_STAGES - 1) & 1));
+            if (tc_elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[s], TC_TILE_BYTES);
+                tma_load_bulk(b_buf + s * TC_TILE_FLOATS, sc.tc_filter + (long long)(c0 + it) * TC_TILE_FLOATS, TC_TILE_BYTES,
+                              &full_bar[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == TC16_MMA_WARP) {
+        const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_buf), TC_M * 16, 128);
+        const uint64_t b_desc0 = tc_smem_desc(smem_u32(b_buf), TC_N * 16, 128);
+        int g = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(&full_bar[s], (unsigned)((it / TC_STAGES) & 1));
+            tc_fence_after();
+            const uint64_t db = b_desc0 + (uint64_t)((s * TC_TILE_BYTES) >> 4);
+#pragma unroll
+            for (int j = 0; j < RT; ++j, ++g) {
+                const int buf = g & 1, use = g >> 1;
+                if (use > 0) mbar_wait(&tempty_bar[buf], (unsigned)((use - 1) & 1));
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
+                const uint64_t da = a_desc0 + (uint64_t)((j * TC_A_BYTES) >> 4);
+                if (tc_elect_one()) {
+                    tc_mma_tf32(acc, da, db, 0u);
+                    tc_mma_tf32(acc, da + (uint64_t)((2 * TC_M * 16) >> 4), db + (uint64_t)((2 * TC_N * 16) >> 4), 1u);
+                    tc_mma_tf32(acc, da + (uint64_t)((4 * TC_M * 16) >> 4), db + (uint64_t)((4 * TC_N * 16) >> 4), 1u);
+                    tc_commit(&tfull_bar[buf]);
+                    if (j == RT - 1) tc_commit(&empty_bar[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        unsigned n_cand = 0;
+        int4 *queue = queues + warp * TC16_QUEUE_CAP;
+        int *q_count = q_counts + warp * 4;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * TC_ACC_STRIDE) + (uint32_t)(sub * 96);
+        uint32_t r[48];
+        int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
+        float k2s[RT];
+        int vc_bits = 0;
+        auto test = [&](float kk, int first, int tri0, int count, int mesh, long long i) {
+            float top[2] = {-3.0e38f, -3.0e38f};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float fa = fabsf(__uint_as_float(r[6 * q + 0])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 2])), fabsf(__uint_as_float(r[6 * q + 4])));
+                const float fb = fabsf(__uint_as_float(r[6 * q + 1])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 3])), fabsf(__uint_as_float(r[6 * q + 5])));
+                top[q & 1] = fmax3_nan(top[q & 1], fa, fb);
+            }
+            const bool some = !(fmax_nan(top[0], top[1]) + kk < 0.0f);
+            if (__any_sync(0xffffffffu, some)) {
+                if (some) {
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int t = 0; t < TC_CHUNK_TRIS; ++t) {
+                        const int c = 6 * (t >> 1) + (t & 1);
+                        const float f = fabsf(__uint_as_float(r[c])) - fmax_nan(fabsf(__uint_as_float(r[c + 2])), fabsf(__uint_as_float(r[c + 4])));
+                        if (!(f + kk < 0.0f)) mask |= 1u << t;
+                    }
+                    const int valid = count - first;
+                    if (valid < TC_CHUNK_TRIS) mask &= valid > 0 ? (1u << valid) - 1u : 0u;
+                    n_cand += __popc(mask);
+                    if (mask && i < rays.n) tc16_enqueue(mask, tri0 + first, i, mesh, queue, q_count, sc, rays, eps, key, cnt);
+                }
+                __syncwarp();
+            }
+        };
+        static_assert(RT % 2 == 0, "the two groups alternate ray tiles");
+        for (int it = 0; it < nt; ++it) {
+            const int4 ti4 = ti_next;
+            if (it + 1 < nt) ti_next = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it + 1));
+            const int tri0 = ti4.x, count = ti4.y, mesh = ti4.z;
+            if (ti4.w != vc_bits) {
+                vc_bits = ti4.w;
+                const float two_vc = 2.0f * __int_as_float(vc_bits);
+#pragma unroll
+                for (int j = 0; j < RT; ++j) {
+                    const long long i = min(ray0 + (long long)j * TC_M, rays.n - 1);
+                    const long long ph = rays.phys(i);
+                    const float4 o = rays.org_pow[ph], d = rays.dir_prev[ph];
+                    k2s[j] = filter_ray_scale_tile(filter_ray_parts(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)), two_vc);
+                }
+            }
+            if (*(volatile int *)q_count >= TC16_QUEUE_DRAIN) tc16_drain(queue, q_count, sc, rays, eps, key, cnt);
+#pragma unroll
+            for (int jj = 0; jj < RT / 2; ++jj) {
+                // own step g = it RT + 2 jj + group: ray tile j = 2 jj + group (k2s is indexed at compile time for both groups)
+                const int g = it * RT + 2 * jj + group;
+                const float kk = group ? k2s[2 * jj + 1] : k2s[2 * jj];
+                const long long i = ray0 + (long long)(2 * jj + group) * TC_M;
+                mbar_wait(&tfull_bar[group], (unsigned)((g >> 1) & 1));
+                tc_fence_after();
+                tc_ld_48(lane_addr, r);
+                tc_wait_ld();
+                test(kk, (2 * sub) * TC_CHUNK_TRIS, tri0, count, mesh, i);
+                tc_ld_48(lane_addr + 48u, r);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (tc_elect_one()) mbar_arrive(&tempty_bar[group]);
+                test(kk, (2 * sub + 1) * TC_CHUNK_TRIS, tri0, count, mesh, i);
+            }
+        }
+        tc16_drain(queue, q_count, sc, rays, eps, key, cnt);
+        if (cand_total) {
+            for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+            if (lane == 0 && n_cand) atomicAdd(cand_total, (unsigned long long)n_cand);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC16_MMA_WARP) tc_free_512(tmem_base);
+}
+
 } // namespace lpcl

@@ -188,14 +188,16 @@ class optical_elements:
         phi2 = phi1 + d_ang
 
         def rot(phi, pts):
-            # R(phi) @ [x, y, 0]^T for every (phi, point) pair -> (len(phi), len(pts), 3)
+            # R(phi) @ [x, y, 0]^T for every (phi, point) pair -> (len(phi), len(pts), 3).  The reference forms the
+            # full 3 x 3 product (geo:289-292): a sum that starts from +0.0, so a component that comes out as -0.0
+            # here (cos(phi) * 0 with cos < 0) is +0.0 there - the final `+ 0.0` maps -0.0 to +0.0, nothing else
             cs, sn = np.cos(phi)[:, None], np.sin(phi)[:, None]
             x, y = pts[None, :, 0], pts[None, :, 1]
             if axis in ("y", "Y"):
-                return np.stack([cs * x, y + 0 * cs, -sn * x], axis=-1)
+                return np.stack([cs * x, y + 0 * cs, -sn * x], axis=-1) + 0.0
             if axis in ("z", "Z"):
-                return np.stack([cs * x - sn * y, sn * x + cs * y, 0 * (cs * x)], axis=-1)
-            return np.stack([x + 0 * cs, cs * y, sn * y], axis=-1)
+                return np.stack([cs * x - sn * y, sn * x + cs * y, 0 * (cs * x)], axis=-1) + 0.0
+            return np.stack([x + 0 * cs, cs * y, sn * y], axis=-1) + 0.0
 
         a1, a2 = rot(phi1, c), rot(phi2, c)  # (K, P, 3)
         quad = np.stack([a1[:, :-1], a1[:, 1:], a2[:, :-1], a2[:, 1:]], axis=2)  # (K, nseg, 4, 3)

@@ -44,8 +44,11 @@ def flatten_light_sources(light_source, lo=None, hi=None):
         o = np.asarray(light.rays_origin, dtype=np.float32)
         d = np.asarray(light.rays_dir, dtype=np.float32)
         p = np.asarray(light.rays_power, dtype=np.float32)
-        if len(o) != int(light.ray_count) or len(d) != int(light.ray_count):
+        if len(o) < int(light.ray_count) or len(d) != int(light.ray_count):
             raise ValueError("light source arrays do not match ray_count")
+        # grid_rays leaves surplus origin rows behind (ls:46-49: sized before ray_count is rounded down to a square);
+        # the reference loop only ever reads rows [0, ray_count) (it:276-283)
+        o = o[: int(light.ray_count)]
         origins.append(o.reshape(-1, 4))
         dirs.append(d.reshape(-1, 4))
         powers.append(p)

@@ -153,13 +153,14 @@ class light_source:
 
     def grid_rays(self):
         """Regular elevation x azimuth grid (reference ls:45-95).  The reference version no
-        longer runs on NumPy >= 1.24 (``np.float``, float ``linspace`` counts); this is the same
-        construction with integer counts.  ``ray_count`` is rounded down to a square."""
+        longer runs on NumPy >= 1.24 (``np.float``, float ``linspace`` counts and subscripts); this is the
+        same construction with integer counts, bit-identical to it (tests/test_refhost_golden.py).
+        ``ray_count`` is rounded down to a square AFTER ``rays_origin`` / ``rays_dest`` were sized (ls:46-49):
+        like the reference's, they keep the original row count - the tracer reads the first ``ray_count``."""
         m = int(np.floor(np.sqrt(self.ray_count)))
         self.rays_origin = np.zeros((self.ray_count, 4)).astype(np.float32) + self.center
-        self.ray_count = m * m
-        self.rays_origin = self.rays_origin[: self.ray_count]
         self.rays_dest = np.zeros((self.ray_count, 4)).astype(np.float32)
+        self.ray_count = m * m
         elevation0 = self._elevation0()
         if self.direction[0] == 0:
             azimuth0 = np.pi / 2.0 if self.direction[1] >= 0 else -np.pi / 2.0
@@ -168,7 +169,9 @@ class light_source:
         el = np.linspace(0.0, np.pi / 2.0, m)
         az = np.linspace(0.0, 2.0 * np.pi, m)
         elevation = np.tile(el, m)[:, None]  # elevation cycles fastest
-        azimuth = np.repeat(az, m)[:, None]
+        azimuth = np.repeat(az, m)
+        azimuth[:m] = az  # ls:72-77: the first block takes the azimuth RAMP, blocks k >= 1 the constant az[k]
+        azimuth = azimuth[:, None]
         self.rays_power = np.array(self.directivity(azimuth, elevation), dtype=np.float32) * self.power
         rd = np.concatenate((np.sin(elevation) * np.cos(azimuth), np.sin(elevation) * np.sin(azimuth),
                              np.cos(elevation), np.zeros((self.ray_count, 1))), axis=1).astype(np.float32)

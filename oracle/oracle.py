@@ -134,8 +134,9 @@ def flatten_sources(light_source):
             origin = np.append(origin, light.rays_origin, axis=0).astype(np.float32)
             direc = np.append(direc, light.rays_dir, axis=0).astype(np.float32)
             power = np.append(power, light.rays_power, axis=0).astype(np.float32)
-    origin = np.ascontiguousarray(np.asarray(origin), dtype=np.float32)
     direc = np.ascontiguousarray(np.asarray(direc), dtype=np.float32)
+    # a single grid_rays source carries surplus origin rows (ls:46-49); the loop slices [0, ray_count) (it:276-283)
+    origin = np.ascontiguousarray(np.asarray(origin)[: len(direc)], dtype=np.float32)
     power = np.asarray(power, dtype=np.float32)
     return origin, direc, power, seq_sum_sorted_f32(power)
 

@@ -159,16 +159,19 @@ def test_three_seams_match_oracle(name):
         g.close()
 
 
-SEARCH_ENV = ("LPCL_SEARCH_IMPL", "LPCL_SEARCH_R", "LPCL_SEARCH_RT", "LPCL_SEARCH_CHUNKS")
+SEARCH_ENV = ("LPCL_SEARCH_IMPL", "LPCL_SEARCH_R", "LPCL_SEARCH_RT", "LPCL_SEARCH_CHUNKS", "LPCL_TC_WARPS")
 
 
 def _set_search(impl, R, chunks):
-    """impl 'simt': R rays per thread; impl 'tc': R ray tiles (128 rays) per CTA; 0 = heuristic."""
+    """impl 'simt': R rays per thread; impl 'tc' / 'tc16' (the thin-warp kernel, LPCL_TC_WARPS=16): R ray tiles
+    (128 rays) per CTA; 0 = heuristic."""
     for k in SEARCH_ENV:
         os.environ.pop(k, None)
-    os.environ["LPCL_SEARCH_IMPL"] = impl
+    os.environ["LPCL_SEARCH_IMPL"] = "tc" if impl == "tc16" else impl
+    if impl == "tc16":
+        os.environ["LPCL_TC_WARPS"] = "16"
     if R:
-        os.environ["LPCL_SEARCH_RT" if impl == "tc" else "LPCL_SEARCH_R"] = str(R)
+        os.environ["LPCL_SEARCH_RT" if impl.startswith("tc") else "LPCL_SEARCH_R"] = str(R)
     if chunks:
         os.environ["LPCL_SEARCH_CHUNKS"] = str(chunks)
 
@@ -180,7 +183,8 @@ def _clear_search():
 
 @pytest.mark.parametrize("impl,R,chunks", [("simt", 1, 1), ("simt", 2, 1), ("simt", 4, 1), ("simt", 1, 7), ("simt", 2, 3),
                                            ("simt", 4, 64), ("tc", 1, 1), ("tc", 2, 1), ("tc", 4, 3), ("tc", 8, 1),
-                                           ("tc", 1, 64), ("tc", 0, 0)])
+                                           ("tc", 1, 64), ("tc", 0, 0), ("tc16", 2, 1), ("tc16", 4, 3), ("tc16", 8, 1),
+                                           ("tc16", 0, 0)])
 def test_search_variants_agree(impl, R, chunks):
     """Both search kernels (packed-FP32 filter, tensor-core filter), their rays-per-CTA variants and
     triangle-range splits (atomic merge) give results identical to the oracle's."""

@@ -31,6 +31,7 @@ def main():
 
     from lightpycl_b200 import _cabi, iterative_tracer as it, scenes
 
+    base_env = {k: v for k, v in os.environ.items() if k.startswith("LPCL_")}
     for wl in args.workloads:
         kw = dict(ray_count=args.rays)
         if wl == "c5_lenslet_array":
@@ -39,7 +40,14 @@ def main():
         if args.iters:
             params = dict(params, trace_iterations=args.iters)
         ref_sig = None
-        for lib in args.libs:
+        for spec in args.libs:
+            # "path.so@NAME=VALUE,NAME2=VALUE2": run-time switches of the library for this run only
+            lib, _, envs = spec.partition("@")
+            for old in [k for k in os.environ if k.startswith("LPCL_") and k not in base_env]:
+                del os.environ[old]
+            os.environ.update(base_env)
+            for kv in filter(None, envs.split(",")):
+                os.environ[kv.split("=")[0]] = kv.split("=")[1]
             _cabi._lib, _cabi.LIB_PATH = None, os.path.abspath(lib)
             tr = it.CL_Tracer(keep_results=False, profile=True)
             tr.prepare(ls, meshes)
@@ -60,7 +68,7 @@ def main():
             ref_sig = ref_sig or sig
             cand = [round(c / max(r, 1), 2) for c, r in zip(tr.stats["candidates"], tr.stats["rays"])]
             print("%-22s %-28s %.3e tests/s  %8.2f ms  search ms/gen %s  cand/ray %s  measured %s %s" % (
-                wl, os.path.basename(lib), tests / (best * 1e-3), best, search[:6], cand[:4], sig,
+                wl, os.path.basename(spec), tests / (best * 1e-3), best, search[:6], cand[:4], sig,
                 "OK" if sig == ref_sig else "MISMATCH vs first lib"), flush=True)
             if args.trace and hasattr(tr._lib, "lpcl_debug_read_trace"):
                 import ctypes as C
