@@ -246,7 +246,7 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ native arm
-def ncu_summary(prefixes=("r2", "r1tc")):
+def ncu_summary(prefixes=("r2b", "r2", "r1tc")):
     """Numbers from the committed `ncu --set full` capture of this workload's search kernel
     (profiles/<prefix>_ncu_traffic.json, written by tools/summarize_ncu.py): DRAM bytes per launch and
     pipe utilisations.  Read-only context for the roofline objects; never a timing source."""

@@ -87,6 +87,7 @@ def test_gpu_post_processing_matches_reference_host_run(name, capsys):
     case, tr, _ = _trace(name)
     z = _load("refhost_trace_%s.npz" % name)
     pts, lim = case["points"], ((-1, 1), (-1, 1))
+    notes = []
     pos, pwr = z["measured_pos"], np.asarray(z["measured_pwr"]).reshape(-1)
     H, xe, ye = tr.get_binned_data(limits=case["limits_xy"], points=pts)
     assert np.array_equal(np.stack([xe, ye]), z["hist_xy_edges"])
@@ -100,8 +101,8 @@ def test_gpu_post_processing_matches_reference_host_run(name, capsys):
         x, y, _ = oracle.project(kind, pos, pwr)
         touched, n_near = _edge_bins(x, y, lim, pts, 2e-6 * 1.6 / (2.0 / pts))
         bad = np.abs(H - want) > 1e-6 * np.abs(want).max()
-        print("%s %s: %d rays near a bin edge, %d bins differ, all of them touched by such a ray: %s"
-              % (name, kind, n_near, int(bad.sum()), bool(np.all(touched[bad]))))
+        notes.append("%s %s: %d measured rays, %d within 2e-6 of a bin edge, %d of %d bins differ by more than 1e-6 (all touched by such a ray: %s)"
+                     % (name, kind, len(pwr), n_near, int(bad.sum()), pts * pts, bool(np.all(touched[bad]))))
         assert np.all(touched[bad]), kind
     H, xe, ye = tr.get_binned_data_replicated(limits=lim, points=pts, axis="z", sources=case["replicas"])
     want = z["hist_replicated"]
@@ -120,4 +121,6 @@ def test_gpu_post_processing_matches_reference_host_run(name, capsys):
     assert abs(total - want[0]) <= 1e-9 * abs(want[0])
     assert np.allclose(np.atleast_1d(angle) / np.pi * 180.0, want[1:1 + n], rtol=2e-8, atol=0)
     assert np.allclose(np.atleast_1d(throughput) * 100.0, want[1 + n:], rtol=2e-8, atol=0)
-    capsys.readouterr()
+    capsys.readouterr()  # the beam metrics print the reference's report lines
+    with capsys.disabled():
+        print("\n" + "\n".join(notes))

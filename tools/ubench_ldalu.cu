@@ -62,8 +62,12 @@ __global__ void k(unsigned *out, unsigned long long *cycles, int reps, float kk)
         if (MODE == 0) {
             ld48(base, rA);
             wait_ld();
+#pragma unroll
+            for (int i = 0; i < 48; ++i) asm volatile("" ::"r"(rA[i]));
             ld48(base + 48u, rB);
             wait_ld();
+#pragma unroll
+            for (int i = 0; i < 48; ++i) asm volatile("" ::"r"(rB[i]));
         } else if (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < 48; ++i) {
@@ -83,16 +87,27 @@ __global__ void k(unsigned *out, unsigned long long *cycles, int reps, float kk)
             for (int i = 0; i < 48; ++i) asm volatile("" : "+r"(rB[i]));
             acc += test48(rB, kk);
             wait_ld();
-        } else {
+        } else if (MODE == 3) {
             ld48(base, rA);
             wait_ld();
             acc += test48(rA, kk);
             ld48(base + 48u, rB);
             wait_ld();
             acc += test48(rB, kk);
+        } else { // MODE 4: the order of search_tc_kernel: wait, test A, load A', test B, load B'
+            wait_ld();
+#pragma unroll
+            for (int i = 0; i < 48; ++i) asm volatile("" : "+r"(rA[i]));
+            acc += test48(rA, kk);
+            ld48(base, rA);
+#pragma unroll
+            for (int i = 0; i < 48; ++i) asm volatile("" : "+r"(rB[i]));
+            acc += test48(rB, kk);
+            ld48(base + 48u, rB);
         }
     }
     const long long t1 = clock64();
+    wait_ld();
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc + rA[5] + rB[7];
     if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -108,14 +123,15 @@ int main()
     cudaMalloc(&out, sms * 1024 * 4);
     cudaMalloc(&cyc, sms * 8);
     unsigned long long hc[148];
-    const char *names[4] = {"load only (2 x 48 columns, wait after each)", "test only (2 chunks)", "pipelined load + test", "serial load, wait, test"};
-    for (int mode = 0; mode < 4; ++mode)
+    const char *names[5] = {"load only (2 x 48 columns, wait after each)", "test only (2 chunks)", "pipelined load + test", "serial load, wait, test", "kernel order: wait, test A, ld A, test B, ld B"};
+    for (int mode = 0; mode < 5; ++mode)
         for (int warps = 4; warps <= 16; warps *= 2) {
             for (int rep = 0; rep < 2; ++rep) {
                 if (mode == 0) k<0><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
                 else if (mode == 1) k<1><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
                 else if (mode == 2) k<2><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
-                else k<3><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
+                else if (mode == 3) k<3><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
+                else k<4><<<sms, warps * 32>>>(out, cyc, reps, -2.0f);
                 cudaDeviceSynchronize();
             }
             cudaMemcpy(hc, cyc, sms * 8, cudaMemcpyDeviceToHost);
