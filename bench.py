@@ -450,7 +450,7 @@ def main_native(args):
                 "the search kernel's CUDA-event time.  frac > 1 is possible because the kernel does not execute that "
                 "formulation: " + ("the packed-FP32 filter executes 19.25 FMA-pipe lane-ops per test" if simt else
                                    "the 15 multiply-adds per test of the filter run on the tensor pipe (roofline), the FP32 "
-                                   "lanes only apply the two product tests to the GEMM output") +
+                                   "lanes only apply the |DEN| - max(|aU|, |aV|) + k >= 0 test to the GEMM output") +
                 "; ncu_fma_pipe_pct is the FMA pipe's utilisation in the committed capture (formulation independent)",
     }
     if simt:
