@@ -171,9 +171,12 @@ def gather_measured(pos_pwr, lineage, per_iter, group, device):
     td.all_gather(lins, lin, group=_pg(group))
     rec_all = torch.cat([r[:c] for r, c in zip(recs, counts)], dim=0)
     lin_all = torch.cat([r[:c] for r, c in zip(lins, counts)], dim=0)
-    # records are iteration-major inside a rank: rank r contributes table[r, i] records of iteration i, in that order
-    iters = torch.arange(n_iter, dtype=torch.int64).repeat(ws)
-    itr_all = torch.repeat_interleave(iters, table[:, :n_iter].reshape(-1)).to(dev)
+    # records are iteration-major inside a rank: rank r contributes table[r, i] records of iteration i, in that order.
+    # The iteration ids are expanded on the communication device (no host pass over the records), as int16: the
+    # second, stable sort then needs a quarter of the radix passes of a 64-bit key
+    total = int(sum(counts))
+    iters = torch.arange(n_iter, dtype=torch.int16, device=dev).repeat(ws)
+    itr_all = torch.repeat_interleave(iters, table[:, :n_iter].reshape(-1).to(dev), output_size=total)
     order = torch.sort(lin_all, stable=True).indices
     order = order[torch.sort(itr_all[order], stable=True).indices]
     return rec_all[order]

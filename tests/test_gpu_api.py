@@ -73,3 +73,30 @@ def test_beam_metrics(traced, capsys):
     elev = np.arccos(pos[:, 2] / np.linalg.norm(pos[:, :3], axis=1))
     w = np.asarray(pwr, np.float64).reshape(-1)
     assert w[elev < np.deg2rad(5)].sum() > 0.9 * w.sum()
+
+
+@pytest.mark.parametrize("name,kw", [("c4_human_eye", dict(ray_count=500, sources=2)),
+                                     ("c5p_lenslet_array_66_meshes", dict(ray_count=300, sources=4, grid=5, ang_pts=9)),
+                                     ("c1_nested_cubes", dict(ray_count=200))])
+def test_device_side_triangle_gather_equals_host_flatten(name, kw, monkeypatch):
+    """The default set-up uploads the INDEXED meshes and gathers v0/v1/v2 on the GPU (index_meshes); with
+    LPCL_DEVICE_GATHER=0 the host gathers (flatten_meshes, it:121-151).  Same device buffers, same trace, same
+    `geometry` attribute - few meshes (one upload per mesh) and many (27 meshes: one concatenated upload)."""
+    from lightpycl_b200 import iterative_tracer as it, scenes
+
+    ls, meshes, params = scenes.CONFIGS[name](**kw)
+    params = dict(params, trace_iterations=min(int(params["trace_iterations"]), 5))
+    tr_dev = it.CL_Tracer()
+    assert tr_dev.device_gather
+    res_dev = tr_dev.iterative_tracer(ls, meshes, **params)
+    monkeypatch.setenv("LPCL_DEVICE_GATHER", "0")
+    tr_host = it.CL_Tracer()
+    assert not tr_host.device_gather
+    res_host = tr_host.iterative_tracer(ls, meshes, **params)
+    for k in ("v0", "v1", "v2"):
+        a, b = tr_dev._scene_tensors[k].cpu().numpy(), tr_host._scene_tensors[k].cpu().numpy()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
+    util.assert_results_equal(list(res_dev), list(res_host), name)
+    assert tr_dev._geometry is None  # not needed for tracing: built on first access
+    for a, b in zip(tr_dev.geometry, tr_host.geometry):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
