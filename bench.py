@@ -383,8 +383,11 @@ def main_native(args):
         times, h2d, d2h, rays_e2e, breakdown, gathered = [], 0, 0, 0, [], 0
         tr2 = it.CL_Tracer(platform_name="NVIDIA", device_name="B200", device=device, keep_results=False,
                            shard_input=strong)
-        tr2.iterative_tracer(ls, meshes, **params)  # warm-up (allocator, scene)
-        tr2.get_measured_rays(gather=strong)
+        # warm-up: the same W untimed steps as the device-resident loop (at least two: host result buffers and device
+        # tensors of step k are still referenced while step k + 1 allocates, so the pools settle after the second step)
+        for _ in range(max(2, args.warmup)):
+            tr2.iterative_tracer(ls, meshes, **params)
+            tr2.get_measured_rays(gather=strong)
         barrier()
         for _ in range(e2e_steps):
             torch.cuda.synchronize(device)
@@ -398,6 +401,10 @@ def main_native(args):
                               "upload_and_scene_ms": round(1e3 * tr2.timings.get("upload_s", 0.0), 2),
                               "device_loop_ms": round(1e3 * tr2.timings.get("run_s", 0.0), 2),
                               "measured_gather_and_download_ms": round(1e3 * (time.perf_counter() - t1), 2)})
+            if os.environ.get("LPCL_GATHER_TIMING") == "1" and strong and world > 1:  # diagnostics (adds synchronisations)
+                from lightpycl_b200 import dist as _d
+
+                breakdown[-1]["gather_phases_ms"] = {k: round(1e3 * v, 2) for k, v in _d.GATHER_TIMINGS.items()}
             h2d = tr2.h2d_bytes
             d2h = int(pos.shape[0] * 16 + 64 * len(tr2.stats["rays"]))
             rays_e2e = sum(tr2.stats["rays"])
@@ -411,7 +418,7 @@ def main_native(args):
         e2e = {"value": e2e_tests / t_e2e, "unit": "tests/s",
                "h2d_bytes_per_step": int(reduce_ranks(float(h2d), "SUM")),
                "d2h_bytes_per_step": int(reduce_ranks(float(d2h), "SUM")),
-               "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
+               "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps, "warmup": max(2, args.warmup),
                "traced_rays_per_s": e2e_tests / tri / t_e2e, "breakdown_per_step_rank0": breakdown,
                "measured_rays": gathered if strong else measured_sum,
                "gather": ("get_measured_rays(gather=True): padded all-gather of every rank's measured records, merged by "

@@ -22,6 +22,9 @@ All helpers work on CPU tensors with the ``gloo`` backend too (used by the CPU t
 
 from __future__ import annotations
 
+import os
+import time
+
 import torch
 
 
@@ -143,6 +146,9 @@ def merge_measured(records, lineages, iter_ids):
     return records[order], lineages[order], iter_ids[order]
 
 
+GATHER_TIMINGS = {}  # LPCL_GATHER_TIMING=1: seconds per phase of the last gather_measured call (synchronising: diagnostics only)
+
+
 def gather_measured(pos_pwr, lineage, per_iter, group, device):
     """All ranks receive every rank's measured records, merged into the reference order.
 
@@ -152,12 +158,23 @@ def gather_measured(pos_pwr, lineage, per_iter, group, device):
     td = _td()
     ws, _ = world(group)
     dev = _comm_device(group, device)
+    timing = os.environ.get("LPCL_GATHER_TIMING") == "1"
+    marks = []
+
+    def mark(name):
+        if timing:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     k = int(pos_pwr.shape[0])
     n_iter = len(per_iter)
     mine = torch.tensor(list(per_iter) + [k], dtype=torch.int64, device=dev)  # per-iteration counts, then the total
     table = [torch.empty_like(mine) for _ in range(ws)]
     td.all_gather(table, mine, group=_pg(group))
     table = torch.stack(table).cpu()
+    mark("counts (first collective: waits for the slowest rank)")
     counts = [int(c) for c in table[:, n_iter]]
     kmax = max(max(counts), 1)
     rec = torch.zeros((kmax, 4), dtype=torch.float32, device=dev)
@@ -169,6 +186,7 @@ def gather_measured(pos_pwr, lineage, per_iter, group, device):
     lins = [torch.empty_like(lin) for _ in range(ws)]
     td.all_gather(recs, rec, group=_pg(group))
     td.all_gather(lins, lin, group=_pg(group))
+    mark("all-gather of records and lineages")
     rec_all = torch.cat([r[:c] for r, c in zip(recs, counts)], dim=0)
     lin_all = torch.cat([r[:c] for r, c in zip(lins, counts)], dim=0)
     # records are iteration-major inside a rank: rank r contributes table[r, i] records of iteration i, in that order.
@@ -179,4 +197,9 @@ def gather_measured(pos_pwr, lineage, per_iter, group, device):
     itr_all = torch.repeat_interleave(iters, table[:, :n_iter].reshape(-1).to(dev), output_size=total)
     order = torch.sort(lin_all, stable=True).indices
     order = order[torch.sort(itr_all[order], stable=True).indices]
-    return rec_all[order]
+    out = rec_all[order]
+    mark("merge (two stable sorts)")
+    if timing:
+        GATHER_TIMINGS.clear()
+        GATHER_TIMINGS.update({b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])})
+    return out
