@@ -170,6 +170,13 @@ typedef struct lpcl_generation {
     int64_t capacity;      /* rays the buffers can hold */
 } lpcl_generation;
 
+/* Tuning hint, not part of the reference interface (it has one kernel, cl:243): which epilogue variant of the
+ * tensor-core search the searches of this scene use from now on.  0 = library default, 8 = eight fat epilogue warps
+ * (search_tc_kernel), 16 = sixteen thin warps in two groups (search_tc16_kernel: faster when many 16-triangle chunk
+ * tests find a candidate).  The results are bit-identical either way; the environment variable LPCL_TC_WARPS, when
+ * set, overrides the hint.  CL_Tracer sets it per generation from the candidate density of the previous one. */
+int lpcl_scene_set_tc_warps(lpcl_scene *scene, int32_t warps);
+
 int64_t lpcl_step_workspace_bytes(const lpcl_scene *scene, int64_t n_rays);
 
 int lpcl_trace_step(const lpcl_scene *scene, const lpcl_generation *parents, const lpcl_generation *children,

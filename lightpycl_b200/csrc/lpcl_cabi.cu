@@ -67,6 +67,7 @@ struct lpcl_scene {
     int64_t owned_bytes = 0;
     int sm_count = 148;
     int device = 0;
+    int tc_warps = 0;           // lpcl_scene_set_tc_warps: 0 = default, 8 / 16 = epilogue variant of the tensor-core search
 };
 
 static_assert(sizeof(StepCounters) == sizeof(lpcl_step_counters), "counter structs must match");
@@ -258,6 +259,14 @@ extern "C" int lpcl_scene_create_in(lpcl_scene **out, const float *d_v0, const f
                              d_scene_mem, scene_mem_bytes, true, stream_);
 }
 
+extern "C" int lpcl_scene_set_tc_warps(lpcl_scene *scene, int32_t warps)
+{
+    if (!scene) return fail(LPCL_E_NULL, "lpcl_scene_set_tc_warps: NULL scene");
+    if (warps != 0 && warps != 8 && warps != 16) return fail(LPCL_E_RANGE, "lpcl_scene_set_tc_warps: warps must be 0, 8 or 16 (got %d)", warps);
+    scene->tc_warps = warps;
+    return 0;
+}
+
 extern "C" void lpcl_scene_destroy(lpcl_scene *scene)
 {
     if (!scene) return;
@@ -357,7 +366,9 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         int tiles_per_chunk = (int)((s->dev.tc_n_tiles + chunks - 1) / chunks);
         chunks = (s->dev.tc_n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
         dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
-        if (env_int("LPCL_TC_WARPS", 8) == 16 && kTc16Variants[v].fn)
+        int tc_warps = env_int("LPCL_TC_WARPS", 0); // the environment (tests, tuning) beats the scene's hint
+        if (tc_warps == 0) tc_warps = s->tc_warps ? s->tc_warps : 8;
+        if (tc_warps == 16 && kTc16Variants[v].fn)
             kTc16Variants[v].fn<<<grid, TC16_THREADS, tc16_smem_bytes(kTc16Variants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
                                                                                                       tiles_per_chunk, cand_total);
         else

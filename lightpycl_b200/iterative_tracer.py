@@ -422,6 +422,9 @@ class CL_Tracer:
         self.shard_input = shard_input
         # LPCL_DEVICE_GATHER=0: gather the per-triangle vertex buffers on the host (flatten_meshes) instead of on the GPU
         self.device_gather = os.environ.get("LPCL_DEVICE_GATHER", "1") != "0"
+        self._candidate_density = None  # filter candidates per (ray, triangle) pair of the last generation traced
+        self._gen0_density, self._gen0_density_tris = None, -1
+        self._tc_warps_set = 0
         self._geometry = None
         self.profile = profile
         self.kernel_times = []
@@ -494,6 +497,7 @@ class CL_Tracer:
             flat["refl"].ctypes.data, flat["diss"].ctypes.data, n_mesh, base, need, self._stream())
         _cabi.check(rc, "lpcl_scene_create_in")
         self._scene = handle
+        self._tc_warps_set = 0  # a fresh handle uses the library default until _pick_search_variant says otherwise
         self._scene_tensors = dev  # the handle borrows the vertex buffers and its own memory: keep them alive
 
     def _get_workspace(self, n):
@@ -708,6 +712,7 @@ class CL_Tracer:
                     hit = torch.empty((n, 4), dtype=torch.int32, device=self.device) if self.record_hits else None
                     self._reserve_measured(self._measured_count + n)
                     ws = self._get_workspace(min(n, tile))
+                    self._pick_search_variant(t_iter)
                     ev = []
                     for lo in range(0, n, tile):
                         hi = min(lo + tile, n)
@@ -753,6 +758,9 @@ class CL_Tracer:
                         self.hit_records.append(hit)
                     self._measured_count += c["n_measured"]
                     self._measured_per_iter.append(c["n_measured"])
+                    self._candidate_density = c["candidates"] / (float(n) * float(self.tri_count))
+                    if t_iter == 0:
+                        self._gen0_density, self._gen0_density_tris = self._candidate_density, int(self.tri_count)
                 else:
                     if self.keep_results:
                         empty = torch.zeros((0, 4), dtype=torch.float32, device=self.device)
@@ -886,6 +894,24 @@ class CL_Tracer:
         gen = _Generation(org_pow[off:], dir_prev[off:], lineage[off:] if lineage is not None else None, n,
                           int(hdr.next_split), int(hdr.next_base))
         return done, (gen if n > 0 else None), False
+
+    # a 16-triangle chunk test of a warp covers 512 (ray, triangle) pairs: above this share of chunk tests that find a
+    # candidate the thin-warp epilogue wins (C2 17 %: +13 %, C4 30 %: +2 %), below it the fat-warp one (C3 2 %, C5 0.6 %)
+    THIN_WARPS_ABOVE = 0.08
+
+    def _pick_search_variant(self, t_iter):
+        """Choose the epilogue variant of the tensor-core search for the next generation from the candidate density the
+        previous generation measured (generation 0: the density generation 0 of this tracer's previous trace of a scene
+        with the same triangle count measured).  Both variants give bit-identical results (lpcl_scene_set_tc_warps)."""
+        if t_iter == 0:
+            known = self._gen0_density if self._gen0_density_tris == int(self.tri_count) else None
+        else:
+            known = self._candidate_density
+        want = 16 if (known is not None and 512.0 * known > self.THIN_WARPS_ABOVE) else 8
+        if want != self._tc_warps_set:
+            _cabi.check(self._lib.lpcl_scene_set_tc_warps(self._scene, want), "lpcl_scene_set_tc_warps")
+            self._tc_warps_set = want
+        self.stats.setdefault("tc_warps", []).append(want)
 
     def _tile_rays(self, n):
         """Rays per tile of a generation of n rays: as many as the scratch budget allows (12 B per
