@@ -103,7 +103,8 @@ def all_reduce_pair(live, power, group, device):
     td = _td()
     t = torch.tensor([float(live), float(power)], dtype=torch.float64, device=_comm_device(group, device))
     td.all_reduce(t, op=td.ReduceOp.SUM, group=_pg(group))
-    return int(round(t[0].item())), float(t[1].item())
+    live_sum, power_sum = t.tolist()  # one device -> host read for both numbers
+    return int(round(live_sum)), float(power_sum)
 
 
 def renumber_lineage(keys, group, device):

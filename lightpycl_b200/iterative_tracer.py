@@ -22,6 +22,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import pickle
+import threading
 import weakref
 from time import strftime, time
 
@@ -557,6 +558,13 @@ class CL_Tracer:
         # it:115 input power = sum(np.sort(power)), a sequential float32 sum over ALL rays: only the
         # termination test needs it, so it is evaluated in run() while generation 0 is on the GPU
         self._power_all = source_powers(light_source)
+        # ... on a helper thread (NumPy releases the GIL in the sort / cumulative sum), started here so that it also
+        # overlaps the upload: on a rank of an 8-GPU run generation 0 is shorter than this sum over ALL rays
+        self._power_thread_result = []
+        self._power_thread = threading.Thread(
+            target=lambda out=self._power_thread_result, p=self._power_all: out.append(float(sorted_sequential_sum_f32(p))),
+            daemon=True)
+        self._power_thread.start()
         self._power_needs_allreduce = False
         self.input_power = None
         pow_shape = None if power.ndim == 1 else power.shape
@@ -629,7 +637,12 @@ class CL_Tracer:
         """Total source power as the reference sums it (it:115); with rays brought per rank, summed
         over the ranks (a collective: every rank calls this at the same point of run())."""
         if self.input_power is None:
-            p = float(sorted_sequential_sum_f32(self._power_all))
+            thread = getattr(self, "_power_thread", None)
+            if thread is not None:
+                thread.join()
+                self._power_thread = None
+            p = self._power_thread_result[0] if getattr(self, "_power_thread_result", None) else \
+                float(sorted_sequential_sum_f32(self._power_all))
             if self._power_needs_allreduce:
                 p = _dist.all_reduce_sum(p, self._group, self.device)
             self.input_power = p
