@@ -385,9 +385,10 @@ def main_native(args):
                            shard_input=strong)
         # warm-up: the same W untimed steps as the device-resident loop (at least two: host result buffers and device
         # tensors of step k are still referenced while step k + 1 allocates, so the pools settle after the second step)
+        pos = pwr = None
         for _ in range(max(2, args.warmup)):
             tr2.iterative_tracer(ls, meshes, **params)
-            tr2.get_measured_rays(gather=strong)
+            pos, pwr = tr2.get_measured_rays(gather=strong)  # held like in the timed loop: the host pool alternates two buffers
         barrier()
         for _ in range(e2e_steps):
             torch.cuda.synchronize(device)

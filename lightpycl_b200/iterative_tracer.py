@@ -423,6 +423,9 @@ class CL_Tracer:
         self.shard_input = shard_input
         # LPCL_DEVICE_GATHER=0: gather the per-triangle vertex buffers on the host (flatten_meshes) instead of on the GPU
         self.device_gather = os.environ.get("LPCL_DEVICE_GATHER", "1") != "0"
+        # LPCL_STREAM_UPLOAD=0: upload all source rays in prepare() instead of slice by slice under generation 0's search
+        self.stream_upload = os.environ.get("LPCL_STREAM_UPLOAD", "1") != "0"
+        self._copy_stream = None
         self._candidate_density = None  # filter candidates per (ray, triangle) pair of the last generation traced
         self._gen0_density, self._gen0_density_tris = None, -1
         self._tc_warps_set = 0
@@ -587,7 +590,15 @@ class CL_Tracer:
                     self._page_lock_if_seen_again(a)
                 host = [torch.from_numpy(a) for a in arrays]
                 job["host"] = host
-                job["origin"], job["dir"], job["power"] = (h.to(self.device, non_blocking=h.is_pinned()) for h in host)
+                # Large ray sets from pageable memory are not uploaded here: run() uploads generation 0 in slices on a copy
+                # stream while the previous slice is being searched (self._stream_slices), which hides ~3 of the 4 ms
+                job["resident"] = not (self.stream_upload and n >= self.STREAM_MIN_RAYS and self.world_size == 1
+                                       and not any(h.is_pinned() for h in host))
+                if job["resident"]:
+                    job["origin"], job["dir"], job["power"] = (h.to(self.device, non_blocking=h.is_pinned()) for h in host)
+                else:
+                    job["origin"], job["dir"], job["power"] = (torch.empty(h.shape, dtype=h.dtype, device=self.device)
+                                                               for h in host)
             self._job = job
         geo_bytes = (sum(v.nbytes + t.nbytes for v, t in flat["parts"]) if "parts" in flat
                      else sum(flat[k].nbytes for k in ("v0", "v1", "v2")))
@@ -688,11 +699,21 @@ class CL_Tracer:
                 org_pow = torch.empty((cap0, 4), dtype=torch.float32, device=self.device)
                 dir_prev = torch.empty((cap0, 4), dtype=torch.float32, device=self.device)
                 lineage = torch.empty(cap0, dtype=torch.int64, device=self.device) if self._lineage else None
-                rc = lib.lpcl_pack_rays(job["origin"].data_ptr(), job["dir"].data_ptr(), job["power"].data_ptr(), None, n,
-                                        job["lineage_base"], org_pow.data_ptr(), dir_prev.data_ptr(),
-                                        lineage.data_ptr() if lineage is not None else None, self._stream())
-                _cabi.check(rc, "lpcl_pack_rays")
-                self.kernel_launches += 1
+                streamed = not job.get("resident", True) and not small
+                if streamed:
+                    # generation 0 arrives slice by slice: slice 0 now, slice k + 1 while slice k is searched (tile loop below)
+                    slices = self._stream_slices(n)
+                    self._upload_slice(job, slices[0], org_pow, dir_prev, lineage, stream)
+                else:
+                    if not job.get("resident", True):  # (a small scene never streams)
+                        for key, h in zip(("origin", "dir", "power"), job["host"]):
+                            job[key].copy_(h)
+                        job["resident"] = True
+                    rc = lib.lpcl_pack_rays(job["origin"].data_ptr(), job["dir"].data_ptr(), job["power"].data_ptr(), None, n,
+                                            job["lineage_base"], org_pow.data_ptr(), dir_prev.data_ptr(),
+                                            lineage.data_ptr() if lineage is not None else None, self._stream())
+                    _cabi.check(rc, "lpcl_pack_rays")
+                    self.kernel_launches += 1
                 if small:
                     # small scene: every generation in ONE launch (csrc/lpcl_small.cuh); the general loop below only
                     # runs if the kernel hands a generation back (the rays multiplied beyond what one SM should trace)
@@ -720,6 +741,12 @@ class CL_Tracer:
                     ch_lin = torch.empty(cap, dtype=torch.int64, device=self.device) if self._lineage else None
                     children = _Generation(ch_org, ch_dir, ch_lin, 0, 0, n)
                     tile = self._tile_rays(n)
+                    tiles = [(lo, min(lo + tile, n)) for lo in range(0, n, tile)]
+                    upload_next = None
+                    if t_iter == 0 and n > 0 and not job.get("resident", True):
+                        tiles = slices  # one ray tile per uploaded slice
+                        tile = max(hi_ - lo_ for lo_, hi_ in tiles)
+                        upload_next = {lo_: sl for (lo_, _), sl in zip(slices, slices[1:])}
                     keep = self.keep_results
                     dest_meas = torch.empty((n if keep else min(n, tile), 4), dtype=torch.float32, device=self.device)
                     hit = torch.empty((n, 4), dtype=torch.int32, device=self.device) if self.record_hits else None
@@ -727,8 +754,8 @@ class CL_Tracer:
                     ws = self._get_workspace(min(n, tile))
                     self._pick_search_variant(t_iter)
                     ev = []
-                    for lo in range(0, n, tile):
-                        hi = min(lo + tile, n)
+                    n_tiles_run = len(tiles)
+                    for lo, hi in tiles:
                         pg = gen.c_struct(lo, hi)
                         cg = children.child_struct(n, c["n_reflect"], c["n_refract"])
                         dm_ptr = dest_meas.data_ptr() + (16 * lo if keep else 0)
@@ -752,6 +779,11 @@ class CL_Tracer:
                             ev[-1][2].record(stream)
                         self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
                         counters_host.copy_(counters_dev, non_blocking=True)
+                        if upload_next is not None:
+                            if lo in upload_next:  # the next slice travels while this one is searched
+                                self._upload_slice(job, upload_next[lo], gen.org_pow, gen.dir_prev, gen.lineage, stream)
+                            else:
+                                job["resident"] = True  # last slice launched: later run() calls find the rays in HBM
                         if lo == 0:
                             self._ensure_input_power()  # host work hidden behind the kernels just launched
                         stream.synchronize()
@@ -791,7 +823,7 @@ class CL_Tracer:
                     live, power_left = _dist.all_reduce_pair(live, power_left, self._group, self.device)
                 for k, v in (("rays", n), ("live", live), ("live_local", live_local), ("power_left", power_left),
                              ("candidates", c["candidates"]), ("measured", c["n_measured"]),
-                             ("terminated", c["n_terminated"]), ("tiles", -(-n // self._tile_rays(n)) if n else 0)):
+                             ("terminated", c["n_terminated"]), ("tiles", n_tiles_run if n else 0)):
                     self.stats[k].append(v)
                 gen = children if (children is not None and children.n > 0) else None
                 if self.verbose:
@@ -925,6 +957,46 @@ class CL_Tracer:
             _cabi.check(self._lib.lpcl_scene_set_tc_warps(self._scene, want), "lpcl_scene_set_tc_warps")
             self._tc_warps_set = want
         self.stats.setdefault("tc_warps", []).append(want)
+
+    STREAM_MIN_RAYS = 1 << 18   # below this a generation 0 is uploaded in one piece
+    STREAM_FIRST = 0.25         # share of the rays in the first slice (its upload is the part nothing hides)
+
+    def _stream_slices(self, n):
+        """[lo, hi) of the slices generation 0 is uploaded and traced in: a first slice of a quarter of the rays (a
+        multiple of 4096), then the rest - its upload (3 ms per 1M rays) hides behind the first slice's search (6 ms) -
+        cut further only where the scratch budget demands it.  Every extra slice costs ~0.5 ms of launch tail and
+        synchronisation, so two beat four (measured: device loop +1.7 ms with four equal slices)."""
+        first = min(max(4096, int(n * self.STREAM_FIRST) // 4096 * 4096), self._tile_rays(n))
+        cuts, lo, cap = [(0, first)], first, self._tile_rays(n)
+        while lo < n:
+            hi = min(lo + cap, n)
+            cuts.append((lo, hi))
+            lo = hi
+        return cuts
+
+    def _upload_slice(self, job, sl, org_pow, dir_prev, lineage, stream):
+        """Host -> device copy of source rays [lo, hi) on the copy stream, packed into the generation-0 buffers there;
+        the compute stream waits for it before the slice's search.  A copy from pageable memory keeps the HOST busy
+        until it is staged, but the GPU goes on with the kernels already queued on the compute stream."""
+        torch = self._torch
+        lo, hi = sl
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if lo == 0:
+            cs.wait_stream(stream)  # the buffers were allocated on the compute stream (idle at this point); the later
+            # slices must NOT wait for the compute stream - the point is to travel while it is busy
+        with torch.cuda.stream(cs):
+            for key, h in zip(("origin", "dir", "power"), job["host"]):
+                job[key][lo:hi].copy_(h[lo:hi], non_blocking=True)
+            rc = self._lib.lpcl_pack_rays(job["origin"].data_ptr() + 16 * lo, job["dir"].data_ptr() + 16 * lo,
+                                          job["power"].data_ptr() + 4 * lo, None, hi - lo, job["lineage_base"] + lo,
+                                          org_pow.data_ptr() + 16 * lo, dir_prev.data_ptr() + 16 * lo,
+                                          lineage.data_ptr() + 8 * lo if lineage is not None else None,
+                                          C.c_void_p(cs.cuda_stream))
+            _cabi.check(rc, "lpcl_pack_rays")
+        self.kernel_launches += 1
+        stream.wait_stream(cs)
 
     def _tile_rays(self, n):
         """Rays per tile of a generation of n rays: as many as the scratch budget allows (12 B per

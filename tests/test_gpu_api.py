@@ -123,3 +123,28 @@ def test_adaptive_search_variant_keeps_results(monkeypatch):
     util.assert_results_equal(list(res3), res1, "fat warps only")
     rc = tr3._lib.lpcl_scene_set_tc_warps(tr3._scene, 12)
     assert rc != 0 and b"warps" in tr3._lib.lpcl_last_error()
+
+
+def test_streamed_upload_of_generation_0_keeps_results(monkeypatch):
+    """Large pageable ray sets are uploaded slice by slice under generation 0's search (LPCL_STREAM_UPLOAD, default on):
+    same `results`, same measured rays, and a second run() on the now-resident rays gives them again."""
+    from lightpycl_b200 import iterative_tracer as it, scenes
+
+    ls, meshes, params = scenes.directivity_lens(ray_count=300_000)
+    params = dict(params, trace_iterations=4)
+    tr = it.CL_Tracer()
+    assert tr.stream_upload and 300_000 >= tr.STREAM_MIN_RAYS
+    res = [tuple(np.array(a) for a in r) for r in tr.iterative_tracer(ls, meshes, **params)]
+    assert tr.stats["tiles"][0] == 2 and tr._job["resident"]
+    pos, pwr = (np.array(a) for a in tr.get_measured_rays())
+    again = tr.run(**params)  # rays resident: one launch for generation 0
+    assert tr.stats["tiles"][0] == 1
+    util.assert_results_equal(list(again), res, "second run on resident rays")
+    monkeypatch.setenv("LPCL_STREAM_UPLOAD", "0")
+    tr0 = it.CL_Tracer()
+    assert not tr0.stream_upload
+    res0 = tr0.iterative_tracer(ls, meshes, **params)
+    assert tr0.stats["tiles"][0] == 1
+    util.assert_results_equal(res, list(res0), "streamed vs one-piece upload")
+    pos0, pwr0 = tr0.get_measured_rays()
+    assert np.array_equal(util.bits(pos), util.bits(np.asarray(pos0))) and np.array_equal(util.bits(pwr), util.bits(np.asarray(pwr0)))
