@@ -485,7 +485,7 @@ def main_native(args):
                     "of both operands quadruples the K = 6 contraction); the contraction itself is 36 flop per test "
                     "(useful_flop_per_test, useful_frac).  The reference's 52 fp32 FLOP/test yardstick is roofline_fp32. "
                     "The kernel is bound by the CUDA-core epilogue that reads the accumulator back (tcgen05.ld) and applies "
-                    "the product tests, not by the tensor pipe (DESIGN.md 4.1)",
+                    "the |DEN| - max(|aU|, |aV|) + k >= 0 test (TMEM read-back, tests and MMAs do not fully overlap on one SM), not by the tensor pipe (DESIGN.md 4.1)",
         }
     roofline.update({"launches": n_search, "avg_launch_ms": search_ms / max(n_search, 1),
                      "tests_per_s_kernel": tests_per_s_kernel,
