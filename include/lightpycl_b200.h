@@ -171,10 +171,12 @@ typedef struct lpcl_generation {
 } lpcl_generation;
 
 /* Tuning hint, not part of the reference interface (it has one kernel, cl:243): which epilogue variant of the
- * tensor-core search the searches of this scene use from now on.  0 = library default, 8 = eight fat epilogue warps
- * (search_tc_kernel), 16 = sixteen thin warps in two groups (search_tc16_kernel: faster when many 16-triangle chunk
- * tests find a candidate).  The results are bit-identical either way; the environment variable LPCL_TC_WARPS, when
- * set, overrides the hint.  CL_Tracer sets it per generation from the candidate density of the previous one. */
+ * tensor-core search the searches of this scene use from now on.  0 = library default: the deferred-flag sweep (one
+ * sign bit per 16-triangle chunk test, no branch in the sweep) followed by a second pass that evaluates every flagged
+ * (ray, chunk) exactly (search_tc_kernel<RT, true> + resolve_records_kernel); 8 = eight fat epilogue warps that vote
+ * after every chunk test and evaluate candidates from per-warp queues (search_tc_kernel<RT, false>); 16 = sixteen thin
+ * warps in two groups (search_tc16_kernel).  The results are bit-identical in every case (the exact evaluation alone
+ * decides); the environment variable LPCL_TC_WARPS, when set, overrides the hint. */
 int lpcl_scene_set_tc_warps(lpcl_scene *scene, int32_t warps);
 
 int64_t lpcl_step_workspace_bytes(const lpcl_scene *scene, int64_t n_rays);

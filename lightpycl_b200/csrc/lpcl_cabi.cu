@@ -54,9 +54,16 @@ struct TcVariant {
     int rt;
     SearchFn fn;
 };
-static const TcVariant kTcVariants[] = {
+typedef void (*SearchRecFn)(SceneDev, RaysDev, float, unsigned long long *, int *, int, unsigned long long *, RecordBuf);
+struct TcRecVariant {
+    int rt;
+    SearchRecFn fn;
+};
+static const TcRecVariant kTcVariants[] = {
     {1, search_tc_kernel<1>}, {2, search_tc_kernel<2>}, {4, search_tc_kernel<4>}, {8, search_tc_kernel<8>}};
 static const int kNumTcVariants = (int)(sizeof(kTcVariants) / sizeof(kTcVariants[0]));
+static const TcRecVariant kTcfVariants[] = { // deferred-flag epilogue
+    {1, search_tc_kernel<1, true>}, {2, search_tc_kernel<2, true>}, {4, search_tc_kernel<4, true>}, {8, search_tc_kernel<8, true>}};
 static const TcVariant kTc16Variants[] = { // LPCL_TC_WARPS=16: two groups of eight thin epilogue warps (RT even; RT = 1 uses the default kernel)
     {1, nullptr}, {2, search_tc16_kernel<2>}, {4, search_tc16_kernel<4>}, {8, search_tc16_kernel<8>}};
 
@@ -226,6 +233,8 @@ static int scene_create_impl(lpcl_scene **out, const float *d_v0, const float *d
     for (int v = 0; v < kNumTcVariants; ++v) {
         SCENE_TRY(cudaFuncSetAttribute(kTcVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        tc_smem_bytes(kTcVariants[v].rt)));
+        SCENE_TRY(cudaFuncSetAttribute(kTcfVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tcf_smem_bytes(kTcfVariants[v].rt)));
         if (kTc16Variants[v].fn)
             SCENE_TRY(cudaFuncSetAttribute(kTc16Variants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            tc16_smem_bytes(kTc16Variants[v].rt)));
@@ -282,10 +291,23 @@ extern "C" int64_t lpcl_scene_device_bytes(const lpcl_scene *s) { return s ? s->
 static int64_t scratch_key_bytes(const lpcl_scene *s, int64_t n) { return align_up((int64_t)s->dev.mesh_count * n * 8, 256); }
 static int64_t scratch_cnt_bytes(const lpcl_scene *s, int64_t n) { return align_up((int64_t)s->dev.mesh_count * n * 4, 256); }
 
+// ... | record header (256 bytes: the append counter) | records: (ray, chunk) pairs the deferred-flag search hands to
+// resolve_records_kernel (lpcl_search_tc.cuh).  Records that do not fit are evaluated inside the search kernel, so the
+// budget per ray is a matter of speed only: LPCL_REC_PER_RAY (default 32 records = 256 bytes per ray; C4 needs 29)
+static int64_t scratch_rec_capacity(int64_t n)
+{
+    static const int per_ray = []() { const char *v = getenv("LPCL_REC_PER_RAY"); int k = v ? atoi(v) : 32; return k < 0 ? 0 : k; }();
+    int64_t cap = n * per_ray;
+    if (per_ray > 0 && cap < 4096) cap = 4096;
+    if (cap > (1LL << 28)) cap = 1LL << 28;
+    return cap;
+}
+static int64_t scratch_rec_bytes(int64_t n) { return 256 + align_up(scratch_rec_capacity(n) * 8, 256); }
+
 extern "C" int64_t lpcl_scratch_bytes(const lpcl_scene *s, int64_t n)
 {
     if (!s || n < 0) return 0;
-    return scratch_key_bytes(s, n) + scratch_cnt_bytes(s, n) + 256;
+    return scratch_key_bytes(s, n) + scratch_cnt_bytes(s, n) + scratch_rec_bytes(n) + 256;
 }
 
 static int64_t step_blocks(int64_t n) { return (n + STEP_RAYS - 1) / STEP_RAYS; }
@@ -312,12 +334,17 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
     unsigned long long *key = (unsigned long long *)d_scratch;
     int *cnt = (int *)((char *)d_scratch + scratch_key_bytes(s, n));
     const long long total = (long long)s->dev.mesh_count * n;
+    RecordBuf records;
+    records.count = (unsigned long long *)((char *)d_scratch + scratch_key_bytes(s, n) + scratch_cnt_bytes(s, n));
+    records.rec = (int2 *)((char *)records.count + 256);
+    records.capacity = scratch_rec_capacity(n);
     const unsigned long long init_key =
         ((unsigned long long)(*reinterpret_cast<const unsigned *>(&max_ray_len)) << 32) | 0xffffffffull;
     {
         long long blocks = (total + 255) / 256;
         if (blocks > (long long)s->sm_count * 32) blocks = (long long)s->sm_count * 32;
-        scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key, zero_a, words_a, zero_b, words_b);
+        scratch_init_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key, cnt, total, init_key, zero_a, words_a, zero_b, words_b,
+                                                                  records.count, 256 / 8);
     }
     // Default: the filter on the tensor cores (lpcl_search_tc.cuh).  LPCL_SEARCH_IMPL=simt selects the
     // packed-FP32 filter (lpcl_search.cuh) - kept as the second implementation the tests cross-check.
@@ -366,14 +393,22 @@ static int launch_search(const lpcl_scene *s, const RaysDev &rays, float max_ray
         int tiles_per_chunk = (int)((s->dev.tc_n_tiles + chunks - 1) / chunks);
         chunks = (s->dev.tc_n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
         dim3 grid((unsigned)ray_blocks, (unsigned)chunks);
-        int tc_warps = env_int("LPCL_TC_WARPS", 0); // the environment (tests, tuning) beats the scene's hint
-        if (tc_warps == 0) tc_warps = s->tc_warps ? s->tc_warps : 8;
+        // epilogue variant: 0 = deferred flags + second pass (default), 8 / 16 = a vote per chunk test, fat / thin warps
+        int tc_warps = env_int("LPCL_TC_WARPS", -1); // the environment (tests, tuning) beats the scene's hint
+        if (tc_warps < 0) tc_warps = s->tc_warps;
         if (tc_warps == 16 && kTc16Variants[v].fn)
             kTc16Variants[v].fn<<<grid, TC16_THREADS, tc16_smem_bytes(kTc16Variants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
                                                                                                       tiles_per_chunk, cand_total);
-        else
+        else if (tc_warps == 8 || tc_warps == 16)
             kTcVariants[v].fn<<<grid, TC_THREADS, tc_smem_bytes(kTcVariants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
-                                                                                              tiles_per_chunk, cand_total);
+                                                                                              tiles_per_chunk, cand_total, records);
+        else {
+            kTcfVariants[v].fn<<<grid, TC_THREADS, tcf_smem_bytes(kTcfVariants[v].rt), stream>>>(s->dev, rays, max_ray_len, key, cnt,
+                                                                                                tiles_per_chunk, cand_total, records);
+            CUDA_TRY(cudaGetLastError());
+            // second pass: the exact evaluation of every flagged (ray, chunk) record, at full occupancy
+            resolve_records_kernel<<<(unsigned)(s->sm_count * 8), 256, 0, stream>>>(s->dev, rays, max_ray_len, key, cnt, records);
+        }
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

@@ -103,6 +103,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
+// the same without suspending: mbarrier.test_wait polled (for a warp whose reaction time is on the critical path)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LPCL_SPIN:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LPCL_SPUN;\n"
+        "bra LPCL_SPIN;\n"
+        "LPCL_SPUN:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// try_wait with the default (implementation-chosen) suspend time
+__device__ __forceinline__ void mbar_wait_short(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LPCL_WS:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LPCL_WSD;\n"
+        "bra LPCL_WS;\n"
+        "LPCL_WSD:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_bulk(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
 {
@@ -163,16 +193,17 @@ __global__ void build_filter_kernel(const float4 *v0, const float4 *v1, const fl
 }
 
 // ------------------------------------------------------------------------------------------ scratch
-// Also clears up to two small 64-bit-word areas (the step counters and the look-back words of the
-// step kernel's chained scan), so that one generation needs no separate memset launches.
+// Also clears up to three small 64-bit-word areas (the step counters, the look-back words of the
+// step kernel's chained scan, the record counter of the deferred-flag search), so that one generation needs no separate memset launches.
 __global__ void scratch_init_kernel(unsigned long long *key, int *cnt, long long total, unsigned long long init_key,
                                     unsigned long long *zero_a, long long words_a, unsigned long long *zero_b,
-                                    long long words_b)
+                                    long long words_b, unsigned long long *zero_c = nullptr, long long words_c = 0)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long k = i; k < words_a; k += stride) zero_a[k] = 0ull;
     for (long long k = i; k < words_b; k += stride) zero_b[k] = 0ull;
+    for (long long k = i; k < words_c; k += stride) zero_c[k] = 0ull;
     for (; i < total; i += stride) {
         key[i] = init_key;
         cnt[i] = 0;

@@ -259,6 +259,72 @@ __device__ __noinline__ void tc_drain(int4 *queue, int *q_count, const SceneDev 
     __syncwarp();
 }
 
+// Deferred-flag epilogue (search_tc_kernel<RT, true>): a record is one flagged (ray, 16-triangle chunk) - 8 bytes:
+// {ray, 4 * tile + chunk}.  The exact evaluation alone decides (the filter only prunes), so results do not depend on
+// which pairs reach it: all (up to 16) triangles of a flagged chunk take it.  Where they take it matters a great deal:
+// inside the sweep the exact evaluation is a chain of L2 latencies run by eight warps per SM, and a warp that is busy
+// with it cannot release its accumulator, which stops the whole SM within a step or two (measured: 4.5 ms of a 23 ms
+// launch on C3, more than the sweep itself on C4).  So the sweep only COLLECTS: a warp's records gather in shared memory
+// and are copied to a record buffer in global memory (one atomicAdd per copy) after the sweep, or when the queue is about
+// to overflow; resolve_records_kernel then evaluates all of them at full occupancy (0.1 - 0.3 ms for the same records).
+// Records that do not fit the buffer are evaluated in place (tc_drain_chunks), so its size is a matter of speed only.
+struct RecordBuf {
+    int2 *rec;                       // capacity records
+    unsigned long long *count;       // records appended so far (may exceed capacity: the excess was evaluated in place)
+    long long capacity;
+};
+
+__device__ __forceinline__ void tc_exact_chunk_lane(const SceneDev &sc, const RaysDev &rays, int2 e, int t, ExactLimits lim,
+                                                    unsigned long long *key, int *cnt)
+{
+    const int4 ti = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (e.y >> 2)); // tri0, count, mesh, Vc
+    const int first = (e.y & 3) * TC_CHUNK_TRIS + t;
+    if (first < ti.y) tc_exact_one(sc, rays, (long long)(unsigned)e.x, ti.x + first, ti.z, lim, key, cnt);
+}
+
+// warp-collective: records [from, *q_count) of the warp's queue, sixteen lanes per record
+__device__ __noinline__ void tc_drain_chunks(const int2 *queue, int from, int total, const SceneDev &sc, const RaysDev &rays,
+                                             ExactLimits lim, unsigned long long *key, int *cnt)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = from + (lane >> 4); k < total; k += 2) tc_exact_chunk_lane(sc, rays, queue[k], lane & 15, lim, key, cnt);
+    __syncwarp();
+}
+
+// warp-collective: the warp's queue -> the global record buffer (what does not fit is evaluated here)
+__device__ __noinline__ void tc_flush_records(int2 *queue, int *q_count, RecordBuf out, const SceneDev &sc, const RaysDev &rays,
+                                              ExactLimits lim, unsigned long long *key, int *cnt)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int total = *(volatile int *)q_count;
+    if (total > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const long long room = out.capacity - (long long)base;
+        const int fits = room >= total ? total : (room > 0 ? (int)room : 0);
+        for (int k = lane; k < fits; k += 32) out.rec[base + k] = queue[k];
+        if (fits < total) tc_drain_chunks(queue, fits, total, sc, rays, lim, key, cnt);
+    }
+    __syncwarp();
+    if (lane == 0) *q_count = 0;
+    __syncwarp();
+}
+
+// second pass of the deferred-flag search: sixteen threads per record, grid-stride
+__global__ void __launch_bounds__(256) resolve_records_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *key,
+                                                              int *cnt, RecordBuf in)
+{
+    const ExactLimits lim = {eps_len(max_ray_len), max_ray_len};
+    const unsigned long long appended = *in.count;
+    const long long total = appended < (unsigned long long)in.capacity ? (long long)appended : in.capacity;
+    const int t = threadIdx.x & 15;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 4;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4; r < total; r += stride)
+        tc_exact_chunk_lane(sc, rays, in.rec[r], t, lim, key, cnt);
+}
+
 // queue full (pathological candidate density): evaluate in place
 __device__ __noinline__ void tc_overflow(unsigned mask, int tri_base, long long i, int mesh, const SceneDev &sc,
                                          const RaysDev &rays, ExactLimits eps, unsigned long long *key, int *cnt)
@@ -297,16 +363,24 @@ __host__ __device__ constexpr int tc_smem_bytes(int rt)
                : 120 * 1024;
 }
 
-template <int RT>
+// deferred-flag epilogue: 8-byte records, a queue that holds a whole sweep in the common case
+__host__ __device__ constexpr int tcf_queue_cap(int rt) { return rt <= 4 ? 1024 : 512; }
+__host__ __device__ constexpr int tcf_smem_bytes(int rt)
+{
+    return TC_STAGES * TC_TILE_BYTES + rt * TC_A_BYTES + TC_EPI_WARPS * (tcf_queue_cap(rt) * 8 + 16) + 256;
+}
+
+template <int RT, bool DEFER = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *__restrict__ key, int *__restrict__ cnt,
-                 int tiles_per_chunk, unsigned long long *cand_total)
+                 int tiles_per_chunk, unsigned long long *cand_total, RecordBuf records)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *b_buf = reinterpret_cast<float *>(smem_raw);
     float *a_buf = reinterpret_cast<float *>(smem_raw + TC_STAGES * TC_TILE_BYTES);
     int4 *queues = reinterpret_cast<int4 *>(smem_raw + TC_STAGES * TC_TILE_BYTES + RT * TC_A_BYTES);
-    int *q_counts = reinterpret_cast<int *>(queues + TC_EPI_WARPS * TC_QUEUE_CAP); // one per 16 bytes
+    constexpr int QUEUE_BYTES = DEFER ? tcf_queue_cap(RT) * 8 : TC_QUEUE_CAP * 16; // per epilogue warp
+    int *q_counts = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(queues) + TC_EPI_WARPS * QUEUE_BYTES); // one per 16 bytes
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(q_counts + TC_EPI_WARPS * 4);
     uint64_t *empty_bar = full_bar + TC_STAGES;
     uint64_t *tfull_bar = empty_bar + TC_STAGES; // [2] accumulator ready   (MMA commit -> epilogue)
@@ -367,7 +441,8 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 }
             }
         }
-        for (int k = lane; k < TC_QUEUE_CAP; k += 32) queues[warp * TC_QUEUE_CAP + k] = make_int4(0, -1, 0, 0);
+        if (!DEFER)
+            for (int k = lane; k < TC_QUEUE_CAP; k += 32) queues[warp * TC_QUEUE_CAP + k] = make_int4(0, -1, 0, 0);
         if (lane == 0) q_counts[warp * 4] = 0;
     }
     fence_async_smem(); // generic-proxy writes of A -> visible to the tensor core's async proxy
@@ -421,6 +496,118 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 TC_STAMP(2, g, 2);
             }
         }
+        if (DEFER && nt > 0) { // the epilogue's wait for the step after the last one
+            if (tc_elect_one()) tc_commit(&tfull_bar[g & 1]);
+            __syncwarp();
+        }
+    } else if (DEFER) {
+        // Deferred-flag epilogue.  The sweep's inner loop has no branch and no vote: a chunk test ends in ONE sign bit
+        // (set = no triangle of the chunk passed), funnel-shifted into a per-lane flag word; the word is examined once
+        // per 4 steps (8 chunk tests), and only then - rarely - flagged (ray, chunk) records go to the warp's queue.
+        // Measured with knock-out builds (profiles/r2c_knockouts.txt): the per-chunk vote + branch of the other
+        // epilogue costs ~70 of its 545 cycles per step although it is almost never taken (the branch waits for the end
+        // of the test's dependency chain and nothing of the next chunk can issue before it), its inlined candidate
+        // code another ~30 (instruction footprint).
+        unsigned n_cand = 0;
+        constexpr int CAP = tcf_queue_cap(RT);
+        int2 *queue = reinterpret_cast<int2 *>(queues) + warp * CAP;
+        int *q_count = q_counts + warp * 4;
+        const int chunk0 = half * 2;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk0 * 48);
+        uint32_t rA[48], rB[48];
+        auto fold = [&](const uint32_t(&r)[48], float kk) -> uint32_t {
+            float top[2] = {-3.0e38f, -3.0e38f};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float fa = fabsf(__uint_as_float(r[6 * q + 0])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 2])), fabsf(__uint_as_float(r[6 * q + 4])));
+                const float fb = fabsf(__uint_as_float(r[6 * q + 1])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 3])), fabsf(__uint_as_float(r[6 * q + 5])));
+                top[q & 1] = fmax3_nan(top[q & 1], fa, fb);
+            }
+            // sign bit clear = a triangle of the chunk passed; a NaN is the canonical one (sign clear): it passes
+            return __float_as_uint(fmax_nan(top[0], top[1]) + kk);
+        };
+        if (nt > 0) {
+            mbar_wait(&tfull_bar[0], 0u);
+            tc_fence_after();
+            tc_ld_48(lane_addr, rA);
+            tc_ld_48(lane_addr + 48u, rB);
+        }
+        int4 ti_next = nt > 0 ? __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + c0) : make_int4(0, 0, 0, 0);
+        float k2s[RT];
+        int vc_bits = 0;
+        unsigned flags = 0xffffffffu;
+        constexpr int CHECK = RT < 4 ? RT : 4;              // steps per examination of the flag word
+        constexpr unsigned CHECK_MASK = (1u << (2 * CHECK)) - 1u;
+        static_assert(32 * 2 * CHECK <= CAP, "one examination must fit the queue");
+        for (int it = 0; it < nt; ++it) {
+            const int4 ti4 = ti_next;
+            if (it + 1 < nt) ti_next = __ldg(reinterpret_cast<const int4 *>(sc.tc_tiles) + (c0 + it + 1));
+            const int count = ti4.y;
+            if (ti4.w != vc_bits) {
+                vc_bits = ti4.w;
+                const float two_vc = 2.0f * __int_as_float(vc_bits);
+#pragma unroll
+                for (int j = 0; j < RT; ++j) k2s[j] = filter_ray_scale_tile(rs[j], two_vc);
+            }
+#pragma unroll
+            for (int j = 0; j < RT; ++j) {
+                const int g = it * RT + j, buf = g & 1;
+                const float k2 = k2s[j];
+                const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
+                tc_wait_ld(); // both chunks of step g are in registers: hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (tc_elect_one()) mbar_arrive(&tempty_bar[buf]);
+                // the accumulator of step g + 1 (the MMA warp commits once more after its last step, so that this wait
+                // needs no "is there a next step" branch; after the last step the loads below fetch stale columns that
+                // nothing reads): with the wait up here nothing separates the two folds from the two loads, and ptxas
+                // interleaves them - the load of the next step's first chunk is in flight during the second fold
+                mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
+                tc_fence_after();
+                flags = __funnelshift_l(fold(rA, k2), flags, 1);
+                tc_ld_48(next_addr, rA);
+                flags = __funnelshift_l(fold(rB, k2), flags, 1);
+                tc_ld_48(next_addr + 48u, rB);
+                if ((j % CHECK) == CHECK - 1) {
+                    // bit b of the low 2 CHECK bits: chunk test number 2 CHECK - 1 - b of the last CHECK steps
+                    const bool some = (~flags & CHECK_MASK) != 0u;
+                    if (__any_sync(0xffffffffu, some)) {
+                        if (*(volatile int *)q_count > CAP - 32 * 2 * CHECK) // no room for every lane's records: flush in mid-sweep
+                            tc_flush_records(queue, q_count, records, sc, rays, eps, key, cnt);
+                        unsigned m = ~flags & CHECK_MASK;
+                        // chunks that are all padding (a mesh's last tile) and rows beyond the last ray are dropped
+                        const int validA = count - chunk0 * TC_CHUNK_TRIS, validB = validA - TC_CHUNK_TRIS;
+                        if (validA <= 0) m &= 0x55555555u; // even test numbers = first chunk = odd bits
+                        if (validB <= 0) m &= 0xaaaaaaaau;
+                        const int j0 = j - (CHECK - 1);
+                        if (m) {
+                            unsigned keep = 0;
+#pragma unroll
+                            for (int q = 0; q < CHECK; ++q)
+                                if (ray0 + (long long)(j0 + q) * TC_M < rays.n) keep |= 3u << (2 * (CHECK - 1 - q));
+                            m &= keep;
+                        }
+                        if (m) {
+                            int pos = atomicAdd(q_count, __popc(m));
+                            n_cand += __popc(m);
+                            while (m) {
+                                const int b = 31 - __clz((int)m);
+                                m &= ~(1u << b);
+                                const int tst = 2 * CHECK - 1 - b; // chunk test number: step j0 + tst / 2, chunk chunk0 + tst % 2
+                                queue[pos++] = make_int2((int)(ray0 + (long long)(j0 + (tst >> 1)) * TC_M), (c0 + it) * 4 + chunk0 + (tst & 1));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        tc_wait_ld();
+        tc_flush_records(queue, q_count, records, sc, rays, eps, key, cnt);
+        if (cand_total) {
+            for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+            if (lane == 0 && n_cand) atomicAdd(cand_total, (unsigned long long)n_cand);
+        }
     } else {
         unsigned n_cand = 0;
         int4 *queue = queues + warp * TC_QUEUE_CAP;
@@ -443,7 +630,7 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 top[q & 1] = fmax3_nan(top[q & 1], fa, fb);
             }
             const bool some = !(fmax_nan(top[0], top[1]) + kk < 0.0f); // rare: a triangle of the chunk passed
-            if (__any_sync(0xffffffffu, some)) { // warp-uniform branch: the common path carries no reconvergence code
+            if (__any_sync(0xffffffffu, some)) { // warp-uniform branch
                 if (some) {
                     unsigned mask = 0; // bit t = triangle `first + t` passed
 #pragma unroll

@@ -940,19 +940,16 @@ class CL_Tracer:
                           int(hdr.next_split), int(hdr.next_base))
         return done, (gen if n > 0 else None), False
 
-    # a 16-triangle chunk test of a warp covers 512 (ray, triangle) pairs: above this share of chunk tests that find a
-    # candidate the thin-warp epilogue wins (C2 17 %: +13 %, C4 30 %: +2 %), below it the fat-warp one (C3 2 %, C5 0.6 %)
-    THIN_WARPS_ABOVE = 0.08
+    # Epilogue variant of the tensor-core search (lpcl_scene_set_tc_warps): 0 = the library default, the deferred-flag
+    # sweep + second pass, which is the fastest one at every candidate density measured (C2 - C5); 8 / 16 = the
+    # variants that vote after every chunk test (fat / thin epilogue warps), kept for cross-checks.
+    SEARCH_VARIANT = 0
 
     def _pick_search_variant(self, t_iter):
-        """Choose the epilogue variant of the tensor-core search for the next generation from the candidate density the
-        previous generation measured (generation 0: the density generation 0 of this tracer's previous trace of a scene
-        with the same triangle count measured).  Both variants give bit-identical results (lpcl_scene_set_tc_warps)."""
-        if t_iter == 0:
-            known = self._gen0_density if self._gen0_density_tris == int(self.tri_count) else None
-        else:
-            known = self._candidate_density
-        want = 16 if (known is not None and 512.0 * known > self.THIN_WARPS_ABOVE) else 8
+        """Tell the scene handle which epilogue variant the next generation's search uses (all give bit-identical
+        results).  Until round 2 the choice followed the candidate density of the previous generation (thin warps above
+        8 % flagged chunk tests); the deferred-flag sweep made it moot."""
+        want = int(self.SEARCH_VARIANT)
         if want != self._tc_warps_set:
             _cabi.check(self._lib.lpcl_scene_set_tc_warps(self._scene, want), "lpcl_scene_set_tc_warps")
             self._tc_warps_set = want

@@ -102,27 +102,24 @@ def test_device_side_triangle_gather_equals_host_flatten(name, kw, monkeypatch):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
-def test_adaptive_search_variant_keeps_results(monkeypatch):
-    """CL_Tracer picks the epilogue variant of the tensor-core search per generation from the candidate density of the
-    previous one (lpcl_scene_set_tc_warps).  A scene dense in candidates (C2: a sixth of the chunk tests find one) switches
-    to the thin-warp kernel after generation 0 - and on the next trace uses it from the start; results do not change."""
+def test_search_variant_hint_keeps_results(monkeypatch):
+    """lpcl_scene_set_tc_warps picks the epilogue variant of the tensor-core search (0 = deferred flags + second pass,
+    the default; 8 / 16 = a vote per chunk test with fat / thin warps); CL_Tracer.SEARCH_VARIANT passes it on.  The
+    results do not depend on it."""
     from lightpycl_b200 import iterative_tracer as it, scenes
 
     ls, meshes, params = scenes.directivity_lens(ray_count=30_000)
     tr = it.CL_Tracer()
     res1 = [tuple(np.array(a) for a in r) for r in tr.iterative_tracer(ls, meshes, **params)]
-    warps1 = list(tr.stats["tc_warps"])
-    assert warps1[0] == 8 and 16 in warps1, warps1
-    res2 = tr.iterative_tracer(ls, meshes, **params)
-    assert tr.stats["tc_warps"][0] == 16, tr.stats["tc_warps"]
-    util.assert_results_equal(list(res2), res1, "second trace (thin warps from generation 0)")
-    monkeypatch.setattr(it.CL_Tracer, "THIN_WARPS_ABOVE", 1e9)  # never switch
-    tr3 = it.CL_Tracer()
-    res3 = tr3.iterative_tracer(ls, meshes, **params)
-    assert set(tr3.stats["tc_warps"]) == {8}
-    util.assert_results_equal(list(res3), res1, "fat warps only")
-    rc = tr3._lib.lpcl_scene_set_tc_warps(tr3._scene, 12)
-    assert rc != 0 and b"warps" in tr3._lib.lpcl_last_error()
+    assert set(tr.stats["tc_warps"]) == {0}, tr.stats["tc_warps"]
+    for variant in (8, 16):
+        monkeypatch.setattr(it.CL_Tracer, "SEARCH_VARIANT", variant)
+        tr2 = it.CL_Tracer()
+        res2 = tr2.iterative_tracer(ls, meshes, **params)
+        assert set(tr2.stats["tc_warps"]) == {variant}
+        util.assert_results_equal(list(res2), res1, "epilogue variant %d" % variant)
+    rc = tr2._lib.lpcl_scene_set_tc_warps(tr2._scene, 12)
+    assert rc != 0 and b"warps" in tr2._lib.lpcl_last_error()
 
 
 def test_streamed_upload_of_generation_0_keeps_results(monkeypatch):

@@ -44,9 +44,9 @@ def _search(tr, origin, direc, max_ray_len, impl):
     near_tri = torch.empty((n, m), dtype=torch.int32, device=tr.device)
     scratch = torch.empty(int(tr._lib.lpcl_scratch_bytes(tr._scene, n)), dtype=torch.uint8, device=tr.device)
     old = os.environ.get("LPCL_SEARCH_IMPL")
-    os.environ["LPCL_SEARCH_IMPL"] = "tc" if impl == "tc16" else impl
-    if impl == "tc16":  # the thin-warp variant of the tensor-core search
-        os.environ["LPCL_TC_WARPS"] = "16"
+    os.environ["LPCL_SEARCH_IMPL"] = "tc" if impl.startswith("tc") else impl
+    if impl in ("tc8", "tc16"):  # the tensor-core search variants that vote per chunk test (fat / thin warps)
+        os.environ["LPCL_TC_WARPS"] = impl[2:]
     try:
         rc = tr._lib.lpcl_intersect(tr._scene, origin.data_ptr(), direc.data_ptr(), n, C.c_float(max_ray_len),
                                     near_t.data_ptr(), hits.data_ptr(), near_tri.data_ptr(), scratch.data_ptr(),
@@ -91,7 +91,7 @@ def test_filtered_searches_equal_exact_search(name, kw, gens):
         origin = gen.logical(gen.org_pow).contiguous()
         direc = gen.logical(gen.dir_prev).contiguous()
         want = _search(tr, origin, direc, mrl, "exact")
-        for impl in ("tc", "tc16", "simt"):
+        for impl in ("tc", "tc8", "tc16", "simt"):
             got = _search(tr, origin, direc, mrl, impl)
             bad = [int((g != w).sum().item()) for g, w in zip(got, want)]
             print("%s generation %d: %d rays x %d triangles, %s vs exact: near_t %d, hits %d, near_tri %d differences"

@@ -163,13 +163,13 @@ SEARCH_ENV = ("LPCL_SEARCH_IMPL", "LPCL_SEARCH_R", "LPCL_SEARCH_RT", "LPCL_SEARC
 
 
 def _set_search(impl, R, chunks):
-    """impl 'simt': R rays per thread; impl 'tc' / 'tc16' (the thin-warp kernel, LPCL_TC_WARPS=16): R ray tiles
-    (128 rays) per CTA; 0 = heuristic."""
+    """impl 'simt': R rays per thread; impl 'tc' (deferred flags + second pass, the default) / 'tc8' / 'tc16' (a vote
+    per chunk test with fat / thin warps, LPCL_TC_WARPS=8 / 16): R ray tiles (128 rays) per CTA; 0 = heuristic."""
     for k in SEARCH_ENV:
         os.environ.pop(k, None)
-    os.environ["LPCL_SEARCH_IMPL"] = "tc" if impl == "tc16" else impl
-    if impl == "tc16":
-        os.environ["LPCL_TC_WARPS"] = "16"
+    os.environ["LPCL_SEARCH_IMPL"] = "tc" if impl.startswith("tc") else impl
+    if impl in ("tc8", "tc16"):
+        os.environ["LPCL_TC_WARPS"] = impl[2:]
     if R:
         os.environ["LPCL_SEARCH_RT" if impl.startswith("tc") else "LPCL_SEARCH_R"] = str(R)
     if chunks:
@@ -183,7 +183,8 @@ def _clear_search():
 
 @pytest.mark.parametrize("impl,R,chunks", [("simt", 1, 1), ("simt", 2, 1), ("simt", 4, 1), ("simt", 1, 7), ("simt", 2, 3),
                                            ("simt", 4, 64), ("tc", 1, 1), ("tc", 2, 1), ("tc", 4, 3), ("tc", 8, 1),
-                                           ("tc", 1, 64), ("tc", 0, 0), ("tc16", 2, 1), ("tc16", 4, 3), ("tc16", 8, 1),
+                                           ("tc", 1, 64), ("tc", 0, 0), ("tc8", 1, 1), ("tc8", 2, 1), ("tc8", 4, 3),
+                                           ("tc8", 8, 1), ("tc8", 0, 0), ("tc16", 2, 1), ("tc16", 4, 3), ("tc16", 8, 1),
                                            ("tc16", 0, 0)])
 def test_search_variants_agree(impl, R, chunks):
     """Both search kernels (packed-FP32 filter, tensor-core filter), their rays-per-CTA variants and
@@ -398,12 +399,15 @@ def test_search_on_adversarial_triangle_soup(seed, scale):
     assert (want[1] > 0).mean() > (0.3 if scale >= 0.05 else 0.1) and (want[1] > 1).sum() > 100
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
-def test_search_with_thousands_of_coincident_triangles(impl):
+@pytest.mark.parametrize("impl,chunks", [("tc", 0), ("tc", 1), ("tc8", 0), ("tc16", 0), ("simt", 0)])
+def test_search_with_thousands_of_coincident_triangles(impl, chunks):
     """Every ray crosses 3,000 copies of the same two triangles (plus a far plate in a second mesh):
     3,000 exact-t ties per ray (the first triangle index must win, cl:278), crossing counts in the
-    thousands, and a candidate density that overflows the tensor-core kernel's per-warp queues, so
-    its in-place overflow evaluation runs too."""
+    thousands, and a candidate density that overflows the tensor-core kernels' per-warp queues, so
+    their overflow paths run too: the in-place evaluation of the per-chunk-vote kernels; for the default
+    deferred-flag kernel the mid-sweep flush of a full queue (chunks = 1: one CTA sweeps all 94 tiles, 6,000
+    records per warp) and the in-kernel evaluation of the records that do not fit the global record buffer
+    (262,500 records against a capacity of 32 per ray)."""
     rng = np.random.RandomState(11)
     copies = 3000
     quad = np.array([[[-1, -1, 5], [1, -1, 5], [1, 1, 5]], [[-1, -1, 5], [1, 1, 5], [-1, 1, 5]]], dtype=np.float64)
@@ -433,7 +437,7 @@ def test_search_with_thousands_of_coincident_triangles(impl):
     assert (want[1][:, 0] == copies).all() and (want[1][:, 1] == 1).all()     # every ray: 3,000 + 1 crossings
     assert (want[2][:, 0] < 2).all()                                             # ties: the first copy wins
     g = GpuSeams(sc)
-    _set_search(impl, 0, 0)
+    _set_search(impl, 0, chunks)
     try:
         got = g.intersect(origin, direc, max_ray_len)
     finally:

@@ -356,3 +356,34 @@ def test_one_launch_trace_of_small_scenes(name, kw, monkeypatch):
         early = _trace_gpu(ls, meshes, params, lineage=True)
         assert 1 <= early.stats["one_launch_generations"] < 4
         util.assert_results_equal(list(early.results), list(general.results), name + " early hand-over")
+
+
+@pytest.mark.parametrize("per_ray", [0, 1])
+def test_record_budget_is_a_matter_of_speed_only(per_ray):
+    """The deferred-flag search hands flagged (ray, chunk) records to its second pass through a buffer in the workspace,
+    LPCL_REC_PER_RAY records per ray (read once per process, hence the subprocess); records that do not fit are evaluated
+    inside the search kernel.  With no buffer at all (0) and with one that overflows (1; C2 flags ~4 chunks per ray) the
+    measured rays are the ones the default budget gives."""
+    import hashlib
+    import subprocess
+    import sys
+
+    code = ("import hashlib, numpy as np\n"
+            "from lightpycl_b200 import iterative_tracer as it, scenes\n"
+            "ls, meshes, params = scenes.directivity_lens(ray_count=20000)\n"
+            "tr = it.CL_Tracer()\n"
+            "tr.iterative_tracer(ls, meshes, **params)\n"
+            "pos, pwr = tr.get_measured_rays()\n"
+            "print('SIG', hashlib.sha1(np.ascontiguousarray(pos).tobytes() + np.ascontiguousarray(pwr).tobytes()).hexdigest(),"
+            " sum(tr.stats['candidates']))\n")
+    sigs = []
+    for env_value in (None, str(per_ray)):
+        env = {k: v for k, v in os.environ.items() if k != "LPCL_REC_PER_RAY"}
+        if env_value is not None:
+            env["LPCL_REC_PER_RAY"] = env_value
+        out = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("SIG ")][-1].split()
+        sigs.append(line[1])
+        assert int(line[2]) > 20000  # more flagged chunks than a budget of one per ray holds
+    assert sigs[0] == sigs[1]
