@@ -652,6 +652,12 @@ extern "C" int lpcl_debug_read_trace(void *h_dst, int64_t bytes) // development 
     CUDA_TRY(cudaMemcpyFromSymbol(h_dst, g_tc_trace, bytes < (int64_t)sizeof(g_tc_trace) ? (size_t)bytes : sizeof(g_tc_trace)));
     return 0;
 }
+extern "C" int lpcl_debug_read_clk(long long *h_dst4)
+{
+    cudaDeviceSynchronize();
+    CUDA_TRY(cudaMemcpyFromSymbol(h_dst4, g_tc_clk, sizeof(g_tc_clk)));
+    return 0;
+}
 #endif
 
 // ------------------------------------------------------------------------------------------ post-processing

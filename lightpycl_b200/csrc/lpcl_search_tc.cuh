@@ -44,9 +44,10 @@ namespace lpcl {
 // lpcl_debug_read_trace (tools/kbench.py --trace)
 constexpr int TC_TRACE_FIRST = 400, TC_TRACE_STEPS = 48, TC_TRACE_SLOTS = 8;
 __device__ long long g_tc_trace[3][TC_TRACE_STEPS][TC_TRACE_SLOTS];
+__device__ long long g_tc_clk[32][4]; // CTA (64 k, 0), k < 32: CTA (0,0): clock64 at start / end, globaltimer (ns) at start / end -> the SM clock under load
 #define TC_STAMP(who, step, slot)                                                                                     \
     do {                                                                                                              \
-        if (trace_on && (step) >= TC_TRACE_FIRST && (step) < TC_TRACE_FIRST + TC_TRACE_STEPS && (threadIdx.x & 31) == 0) \
+        if (trace_on && ((who) == 2 || (warp & 3) == 0) && (step) >= TC_TRACE_FIRST && (step) < TC_TRACE_FIRST + TC_TRACE_STEPS && (threadIdx.x & 31) == 0) \
             g_tc_trace[who][(step) - TC_TRACE_FIRST][slot] = clock64();                                             \
     } while (0)
 #else
@@ -115,9 +116,15 @@ __global__ void build_tc_kernel(const float4 *v0, const float4 *v1, const float4
     if (j < ti.count) {
         float4 a = v0[ti.tri0 + j], b = v1[ti.tri0 + j], c = v2[ti.tri0 + j];
         r = make_tc_rows(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), __int_as_float(ti.pad));
-    } else { // padding: never read back (the epilogue stops at ti.count)
+    } else {
+        // padding slot of a mesh's last tile: rows that fail the filter, DEN' = 0 and |aU'|, |aV'| = 2^40 |a . D| for two
+        // fixed directions a (a zero row would PASS - 0 + k >= 0 - and every ray would carry a record for every padded
+        // chunk into the second pass).  A ray along (3, -1, -2) still passes; the exact pass looks at valid slots only
         for (int q = 0; q < 3; ++q)
             for (int k = 0; k < 6; ++k) r.c[q][k] = 0.0f;
+        const float big = 1099511627776.0f; // 2^40: above any margin k = 1.6e-5 |D| (|O| + 2 Vc), far below overflow
+        r.c[1][3] = big, r.c[1][4] = big, r.c[1][5] = big;         // aU' = 2^40 (Dx + Dy + Dz)
+        r.c[2][3] = big, r.c[2][4] = -big, r.c[2][5] = 2.0f * big;  // aV' = 2^40 (Dx - Dy + 2 Dz)
     }
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -163,11 +170,12 @@ __device__ __forceinline__ uint64_t tc_smem_desc(unsigned addr, unsigned lbo_byt
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate,
+                                            uint32_t idesc = TC_IDESC)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-                 "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
 // arrives on the mbarrier when every MMA issued so far by this thread has completed
@@ -509,6 +517,12 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
         // of the test's dependency chain and nothing of the next chunk can issue before it), its inlined candidate
         // code another ~30 (instruction footprint).
         unsigned n_cand = 0;
+#ifdef LPCL_TC_TRACE
+        if (blockIdx.y == 0 && (blockIdx.x & 63) == 0 && blockIdx.x < 2048 && warp == 0 && lane == 0) {
+            g_tc_clk[blockIdx.x >> 6][0] = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tc_clk[blockIdx.x >> 6][2]));
+        }
+#endif
         constexpr int CAP = tcf_queue_cap(RT);
         int2 *queue = reinterpret_cast<int2 *>(queues) + warp * CAP;
         int *q_count = q_counts + warp * 4;
@@ -554,20 +568,28 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 const int g = it * RT + j, buf = g & 1;
                 const float k2 = k2s[j];
                 const uint32_t next_addr = lane_addr + (uint32_t)((buf ^ 1) * TC_ACC_STRIDE);
+                TC_STAMP(half, g, 0);
                 tc_wait_ld(); // both chunks of step g are in registers: hand the accumulator back
+                TC_STAMP(half, g, 1);
                 tc_fence_before();
                 __syncwarp();
                 if (tc_elect_one()) mbar_arrive(&tempty_bar[buf]);
+                TC_STAMP(half, g, 2);
                 // the accumulator of step g + 1 (the MMA warp commits once more after its last step, so that this wait
                 // needs no "is there a next step" branch; after the last step the loads below fetch stale columns that
                 // nothing reads): with the wait up here nothing separates the two folds from the two loads, and ptxas
                 // interleaves them - the load of the next step's first chunk is in flight during the second fold
                 mbar_wait(&tfull_bar[buf ^ 1], (unsigned)(((g + 1) >> 1) & 1));
+                TC_STAMP(half, g, 3);
                 tc_fence_after();
                 flags = __funnelshift_l(fold(rA, k2), flags, 1);
+                TC_STAMP(half, g, 4);
                 tc_ld_48(next_addr, rA);
+                TC_STAMP(half, g, 5);
                 flags = __funnelshift_l(fold(rB, k2), flags, 1);
+                TC_STAMP(half, g, 6);
                 tc_ld_48(next_addr + 48u, rB);
+                TC_STAMP(half, g, 7);
                 if ((j % CHECK) == CHECK - 1) {
                     // bit b of the low 2 CHECK bits: chunk test number 2 CHECK - 1 - b of the last CHECK steps
                     const bool some = (~flags & CHECK_MASK) != 0u;
@@ -603,6 +625,12 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
             }
         }
         tc_wait_ld();
+#ifdef LPCL_TC_TRACE
+        if (blockIdx.y == 0 && (blockIdx.x & 63) == 0 && blockIdx.x < 2048 && warp == 0 && lane == 0) {
+            g_tc_clk[blockIdx.x >> 6][1] = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tc_clk[blockIdx.x >> 6][3]));
+        }
+#endif
         tc_flush_records(queue, q_count, records, sc, rays, eps, key, cnt);
         if (cand_total) {
             for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
