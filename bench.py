@@ -246,7 +246,7 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ native arm
-def ncu_summary(prefixes=("r2b", "r2", "r1tc")):
+def ncu_summary(prefixes=("r2c", "r2b", "r2", "r1tc")):
     """Numbers from the committed `ncu --set full` capture of this workload's search kernel
     (profiles/<prefix>_ncu_traffic.json, written by tools/summarize_ncu.py): DRAM bytes per launch and
     pipe utilisations.  Read-only context for the roofline objects; never a timing source."""
@@ -484,8 +484,10 @@ def main_native(args):
             "note": "144 = the tensor-core flops this formulation ISSUES per test (3 outputs x K 24 x 2: the hi/lo TF32 split "
                     "of both operands quadruples the K = 6 contraction); the contraction itself is 36 flop per test "
                     "(useful_flop_per_test, useful_frac).  The reference's 52 fp32 FLOP/test yardstick is roofline_fp32. "
-                    "The kernel is bound by the CUDA-core epilogue that reads the accumulator back (tcgen05.ld) and applies "
-                    "the |DEN| - max(|aU|, |aV|) + k >= 0 test (TMEM read-back, tests and MMAs do not fully overlap on one SM), not by the tensor pipe (DESIGN.md 4.1)",
+                    "avg_launch_ms is one lpcl_trace_search call: scratch initialisation + the deferred-flag sweep "
+                    "(search_tc_kernel) + its second pass (resolve_records_kernel, ~1 % on C3).  What keeps the sweep off "
+                    "the tensor peak: TMEM read-back, chunk tests and MMAs share one SM (DESIGN.md 4.1), and the SM clock "
+                    "under this kernel is 1.82 - 1.84 of 1.965 GHz (sw_power_cap; `clocks`)",
         }
     roofline.update({"launches": n_search, "avg_launch_ms": search_ms / max(n_search, 1),
                      "tests_per_s_kernel": tests_per_s_kernel,

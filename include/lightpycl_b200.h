@@ -178,6 +178,9 @@ typedef struct lpcl_generation {
  * warps in two groups (search_tc16_kernel).  The results are bit-identical in every case (the exact evaluation alone
  * decides); the environment variable LPCL_TC_WARPS, when set, overrides the hint. */
 int lpcl_scene_set_tc_warps(lpcl_scene *scene, int32_t warps);
+/* Kernel launches one lpcl_trace_search / lpcl_intersect call issues under the scene's current hint and the environment
+ * (2 = scratch initialisation + search; 3 = + the second pass of the deferred-flag search).  For launch accounting. */
+int32_t lpcl_search_launch_count(const lpcl_scene *scene);
 
 int64_t lpcl_step_workspace_bytes(const lpcl_scene *scene, int64_t n_rays);
 

@@ -71,6 +71,7 @@ SYMBOLS = {
     "lpcl_scene_bytes": (_i64, [_i32, _i32]),
     "lpcl_scene_create_in": (C.c_int, [C.POINTER(_p), _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     "lpcl_scene_set_tc_warps": (C.c_int, [_p, _i32]),
+    "lpcl_search_launch_count": (_i32, [_p]),
     "lpcl_scene_destroy": (None, [_p]),
     "lpcl_scene_tri_count": (_i32, [_p]),
     "lpcl_scene_mesh_count": (_i32, [_p]),

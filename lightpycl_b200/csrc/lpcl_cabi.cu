@@ -276,6 +276,18 @@ extern "C" int lpcl_scene_set_tc_warps(lpcl_scene *scene, int32_t warps)
     return 0;
 }
 
+static int env_int(const char *name, int dflt);
+
+extern "C" int32_t lpcl_search_launch_count(const lpcl_scene *scene)
+{
+    if (!scene) return 0;
+    const char *impl = getenv("LPCL_SEARCH_IMPL");
+    if (impl && (strcmp(impl, "exact") == 0 || strcmp(impl, "simt") == 0)) return 2;
+    int tc_warps = env_int("LPCL_TC_WARPS", -1);
+    if (tc_warps < 0) tc_warps = scene->tc_warps;
+    return tc_warps == 8 || tc_warps == 16 ? 2 : 3;
+}
+
 extern "C" void lpcl_scene_destroy(lpcl_scene *scene)
 {
     if (!scene) return;

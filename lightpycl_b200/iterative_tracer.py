@@ -777,7 +777,8 @@ class CL_Tracer:
                         _cabi.check(rc, "lpcl_trace_resolve")
                         if prof:
                             ev[-1][2].record(stream)
-                        self.kernel_launches += 3  # scratch init, search, fused resolve/Fresnel/compaction
+                        # scratch init, search (+ its second pass), fused resolve/Fresnel/compaction
+                        self.kernel_launches += int(lib.lpcl_search_launch_count(self._scene)) + 1
                         counters_host.copy_(counters_dev, non_blocking=True)
                         if upload_next is not None:
                             if lo in upload_next:  # the next slice travels while this one is searched
