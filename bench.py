@@ -259,8 +259,10 @@ def ncu_summary(prefixes=("r2c", "r2b", "r2", "r1tc")):
             continue
         for k in ("search_tc_kernel", "search_kernel", "step_kernel"):
             if k in cap.get("kernels", {}) and not out[k]:
-                v = cap["kernels"][k][0]
-                tot = v.get("dram_read_bytes", float("nan")) + v.get("dram_write_bytes", float("nan"))
+                # a capture of a streamed-upload trace holds one generation as several slice launches: their bytes add up
+                parts = cap["kernels"][k][: int(cap.get("slices_of_one_generation", 1))]
+                v = parts[-1]
+                tot = sum(q.get("dram_read_bytes", float("nan")) + q.get("dram_write_bytes", float("nan")) for q in parts)
                 out[k] = {"traffic": tot if tot == tot else None, "fma_pipe_pct": v.get("fma_pipe_pct"),
                           "tensor_pipe_pct": v.get("tensor_pipe_pct"), "issue_pct": v.get("issue_pct"),
                           "file": "profiles/" + pre + "_ncu_traffic.json"}

@@ -194,7 +194,8 @@ int lpcl_trace_step(const lpcl_scene *scene, const lpcl_generation *parents, con
  * nearest-hit search into the workspace and adds its candidate count to d_counters->candidates;
  * lpcl_trace_resolve runs the fused media-resolution / Fresnel / compaction kernel on the workspace
  * lpcl_trace_search just filled for the same parents and accumulates into d_counters.
- * lpcl_trace_step == search + resolve: three kernel launches, no memsets. */
+ * lpcl_trace_step == search + resolve: three kernel launches (four with the default search, whose second pass is its
+ * own launch; lpcl_search_launch_count), no memsets. */
 int lpcl_trace_search(const lpcl_scene *scene, const lpcl_generation *parents, void *d_workspace,
                       float max_ray_len, lpcl_step_counters *d_counters, void *stream);
 int lpcl_trace_resolve(const lpcl_scene *scene, const lpcl_generation *parents, const lpcl_generation *children,

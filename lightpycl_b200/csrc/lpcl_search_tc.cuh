@@ -321,7 +321,7 @@ __device__ __noinline__ void tc_flush_records(int2 *queue, int *q_count, RecordB
 }
 
 // second pass of the deferred-flag search: sixteen threads per record, grid-stride
-__global__ void __launch_bounds__(256) resolve_records_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *key,
+__global__ void __launch_bounds__(256, 8) resolve_records_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long long *key,
                                                               int *cnt, RecordBuf in)
 {
     const ExactLimits lim = {eps_len(max_ray_len), max_ray_len};

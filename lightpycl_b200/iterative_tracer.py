@@ -437,6 +437,7 @@ class CL_Tracer:
         self._scene = None
         self._scene_tensors = None
         self._workspace = None
+        self._scratch_per_ray = None
         self.timings = {}
         self.stats = {}
 
@@ -502,6 +503,7 @@ class CL_Tracer:
         _cabi.check(rc, "lpcl_scene_create_in")
         self._scene = handle
         self._tc_warps_set = 0  # a fresh handle uses the library default until _pick_search_variant says otherwise
+        self._scratch_per_ray = None
         self._scene_tensors = dev  # the handle borrows the vertex buffers and its own memory: keep them alive
 
     def _get_workspace(self, n):
@@ -997,9 +999,14 @@ class CL_Tracer:
         stream.wait_stream(cs)
 
     def _tile_rays(self, n):
-        """Rays per tile of a generation of n rays: as many as the scratch budget allows (12 B per
-        ray and mesh + the per-tile end points), in multiples of 4096, at least 65,536."""
-        per_ray = 12 * int(self.mesh_count) + 16 + 1
+        """Rays per tile of a generation of n rays: as many as the scratch budget allows (per ray: 12 B per mesh of
+        search results + the record budget of the deferred-flag search, as the library sizes them, + the per-tile end
+        points), in multiples of 4096, at least 65,536."""
+        if self._scratch_per_ray is None:  # marginal workspace bytes per ray, from the library's own sizing
+            m = 1 << 20
+            grow = int(self._lib.lpcl_step_workspace_bytes(self._scene, 2 * m)) - int(self._lib.lpcl_step_workspace_bytes(self._scene, m))
+            self._scratch_per_ray = max(12 * int(self.mesh_count), -(-grow // m))
+        per_ray = self._scratch_per_ray + 16 + 1
         tile = max(65536, (self.ray_tile_bytes // per_ray) // 4096 * 4096)
         return n if n <= tile else tile
 

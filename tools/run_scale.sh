@@ -1,7 +1,7 @@
 #!/bin/bash
-# usage: tools/run_scale.sh N WORKLOAD RAYS STEPS WARMUP [extra bench.py flags]   -> gpurun_out/r2_scale_<workload>_n<N>.json
+# usage: tools/run_scale.sh N WORKLOAD RAYS STEPS WARMUP [extra bench.py flags]   -> gpurun_out/r2c_scale_<workload>_n<N>.json
 N=$1; WL=$2; RAYS=$3; STEPS=$4; WARM=$5; shift 5
-OUT=gpurun_out/r2b_scale_${WL}_n${N}
+OUT=gpurun_out/r2c_scale_${WL}_n${N}
 if [ "$N" = "1" ]; then
   python bench.py --gpus 1 --workload $WL --rays $RAYS --steps $STEPS --warmup $WARM "$@" > $OUT.json 2> $OUT.err
 else
