@@ -11,19 +11,23 @@
 // K-slots carry the four partial products of the hi/lo TF32 split of the six ray numbers (M, D)
 // and of the triangle's scaled coefficients.  The accumulator lives in TMEM (two 192-column
 // buffers, so the MMAs of the next ray tile overlap the epilogue of this one); the epilogue warps
-// read it back with tcgen05.ld (lane = ray, 6 consecutive columns = one pair of triangles), apply
-// the two sign-agnostic tests in their square form with packed FP32 (3 x fma.rn.f32x2 + 2 x LOP3
-// per PAIR of triangles - the 15 FMAs per test of the SIMT kernel are gone) and hand the rare
-// candidates to the exact, reference-ordered evaluation, which alone decides results.
+// read it back with tcgen05.ld (lane = ray, 6 consecutive columns = one pair of triangles) and apply
+// the sign-agnostic test in its linear form, |DEN'| - max(|aU'|, |aV'|) + k >= 0 (FMNMX + FADD per
+// triangle, one FMNMX3 per pair to fold a 16-triangle chunk; the 15 FMAs per test of the SIMT kernel
+// are gone).  Only the exact, reference-ordered evaluation decides results; who runs it differs:
+//   search_tc_kernel<RT, true> (default)  the sweep keeps ONE sign bit per chunk test in a per-lane flag
+//              word - no vote, no branch in the inner loop - and, once per tile, appends flagged (ray, chunk)
+//              records to a queue; the records go to global memory and resolve_records_kernel evaluates
+//              every triangle of every flagged chunk at full occupancy (a second launch);
+//   search_tc_kernel<RT, false>, search_tc16_kernel (LPCL_TC_WARPS=8 / 16, round 2b)  vote after every chunk
+//              test, recompute the per-triangle mask in the rare branch, queue (ray, triangle) candidates
+//              per warp and drain them inside the kernel.
 //
 // CTA = 10 warps, one CTA per SM:
 //   warps 0-7  epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its rays) and the two
-//              16-triangle chunks of half w / 4 of EVERY (ray tile, triangle tile) step, software
-//              pipelined over two 48-register buffers (the tcgen05.ld of the next chunk is in flight
-//              while this one is tested).  Few fat warps keep the per-step overhead (barrier wait,
-//              fences, release) per SM sub-partition small - the sub-partition's issue slots, not
-//              the tensor pipe, are the scarce resource (profiles/r1_tc_notes.txt).  The epilogue
-//              warps also stage the A operand (RT ray tiles) once per CTA;
+//              16-triangle chunks of half w / 4 of EVERY (ray tile, triangle tile) step through two
+//              48-register buffers (the tcgen05.ld of the next step's chunks are in flight while this
+//              step's are folded).  The epilogue warps also stage the A operand (RT ray tiles) once per CTA;
 //   warp 8     TMA producer: one bulk copy (18 KB) per triangle tile, TC_STAGES deep;
 //   warp 9     MMA issuer (one elected lane): waits tile + free accumulator, issues 3 MMAs, commits.
 // Shared-memory operands use the no-swizzle K-major canonical layout (8-row x 16-byte core
@@ -537,7 +541,8 @@ search_tc_kernel(SceneDev sc, RaysDev rays, float max_ray_len, unsigned long lon
                 const float fb = fabsf(__uint_as_float(r[6 * q + 1])) - fmax_nan(fabsf(__uint_as_float(r[6 * q + 3])), fabsf(__uint_as_float(r[6 * q + 5])));
                 top[q & 1] = fmax3_nan(top[q & 1], fa, fb);
             }
-            // sign bit clear = a triangle of the chunk passed; a NaN is the canonical one (sign clear): it passes
+            // sign bit clear = a triangle of the chunk passed, exactly the other kernels' !(x + k < 0): a NaN is the
+            // canonical one (sign clear) and passes; -0 cannot occur (|DEN| - m is +0 when they are equal, k >= +0)
             return __float_as_uint(fmax_nan(top[0], top[1]) + kk);
         };
         if (nt > 0) {

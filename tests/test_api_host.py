@@ -218,3 +218,28 @@ def test_a_held_result_survives_later_calls():
         p2, w2 = CL_Tracer._host_result_arrays(t, 1000)
         p2[:], w2[:] = 0.0, 0.0
     assert np.all(xyz == 3.0) and np.all(pwr == 4.0)
+
+
+def test_ray_tile_size_follows_the_library_workspace_sizing():
+    """CL_Tracer._tile_rays: rays per tile = ray_tile_bytes / (marginal workspace bytes per ray as the LIBRARY sizes them -
+    12 B per mesh of search results + the record budget of the deferred-flag search - + the per-tile end points), in
+    multiples of 4096, at least 65,536; a generation that fits is not tiled.  No GPU: the library is a stand-in."""
+    from lightpycl_b200 import iterative_tracer as it
+
+    class FakeLib:
+        calls = 0
+
+        def lpcl_step_workspace_bytes(self, scene, n):
+            FakeLib.calls += 1
+            return 3 * 12 * n + 256 + 8 * 32 * n + 4096  # key + count for 3 meshes, 32 records of 8 bytes per ray
+
+    tr = object.__new__(it.CL_Tracer)
+    tr._lib, tr._scene, tr.mesh_count, tr._scratch_per_ray = FakeLib(), None, 3, None
+    tr.ray_tile_bytes = 1 << 30
+    per_ray = 36 + 256 + 17
+    want = ((1 << 30) // per_ray) // 4096 * 4096
+    assert tr._tile_rays(10 * want) == want
+    assert tr._tile_rays(want) == want and tr._tile_rays(1000) == 1000
+    assert FakeLib.calls == 2  # sized once per scene
+    tr.ray_tile_bytes = 1
+    assert tr._tile_rays(1_000_000) == 65536
