@@ -478,8 +478,12 @@ def main_native(args):
             "unit": "TFLOP/s", "frac": tc_tflops / tf32_peak if tf32_peak else None,
             "traffic": ncu[kname].get("traffic"), "traffic_note": "dram read+write bytes per launch, ncu --set full (%s); "
             "algorithmic DRAM bytes per launch = 32 B/ray + 288 B/triangle + results" % ncu[kname].get("file"),
-            "peak_source": "kind::tf32 tcgen05.mma runs at half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2 "
-                           "(tools/ubench_tmem.cu measures 4092 tf32 flop/clk/SM = 1190 TFLOP/s at 1965 MHz unthrottled)",
+            "peak_source": "kind::tf32 tcgen05.mma runs at half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2, the BURST "
+                           "figure (the stricter denominator; peak_sustained / frac_sustained use bf16_tflops_sustained / 2, the "
+                           "figure for a kernel inside a long step; tools/ubench_tmem.cu measures 4092 tf32 flop/clk/SM = 1190 "
+                           "TFLOP/s at 1965 MHz unthrottled)",
+            "peak_sustained": float(peaks.get("bf16_tflops_sustained", 0.0)) / 2.0 or None,
+            "frac_sustained": (tc_tflops / (float(peaks["bf16_tflops_sustained"]) / 2.0)) if peaks.get("bf16_tflops_sustained") else None,
             "algorithmic_flop_per_test": tc_flop, "useful_flop_per_test": 36.0,
             "useful_frac": 36.0 * tests_per_s_kernel / 1e12 / tf32_peak if tf32_peak else None,
             "ncu_tensor_pipe_pct": ncu[kname].get("tensor_pipe_pct"),
