@@ -134,8 +134,42 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.stop_flag, self.source = None, False, "nvidia-smi -lms 100"
+
+    def _start_nvml(self):
+        """In-process NVML sampling every ~5 ms: nvidia-smi needs a few hundred ms before its first line, longer than the
+        whole timed region of a sharded run (8 GPUs: 5 traces of 6 ms).  Any failure falls back to nvidia-smi."""
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(self.index))
+        smax = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)  # fail here, not in the thread
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row slot
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    row = [str(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)), str(smax),
+                           str(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0), "", "", "", ""]
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                    for bit, slot in bits:
+                        row[slot] = "Active" if mask & bit else "Not Active"
+                    self.rows.append(row)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+
+        self.nvml = threading.Thread(target=loop, daemon=True)
+        self.nvml.start()
+        self.source = "NVML, every 5 ms"
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -150,13 +184,17 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.nvml.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
@@ -174,7 +212,7 @@ class ClockSampler:
             pmax = max(power)
             loaded = [c for c, p in zip(sm, power) if p >= 0.5 * pmax] or sm
             return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                    "samples": len(sm), "power_w_max": pmax}
+                    "samples": len(sm), "power_w_max": pmax, "source": self.source}
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
 
 
