@@ -145,6 +145,8 @@ class ClockSampler:
         handle = pynvml.nvmlDeviceGetHandleByIndex(int(self.index))
         smax = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
         pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)  # fail here, not in the thread
+        pynvml.nvmlDeviceGetPowerUsage(handle)
+        pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
         bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row slot
 
         def loop():
