@@ -112,11 +112,13 @@ def test_search_variant_hint_keeps_results(monkeypatch):
     tr = it.CL_Tracer()
     res1 = [tuple(np.array(a) for a in r) for r in tr.iterative_tracer(ls, meshes, **params)]
     assert set(tr.stats["tc_warps"]) == {0}, tr.stats["tc_warps"]
+    assert tr._lib.lpcl_search_launch_count(tr._scene) == 3  # scratch initialisation, sweep, second pass
     for variant in (8, 16):
         monkeypatch.setattr(it.CL_Tracer, "SEARCH_VARIANT", variant)
         tr2 = it.CL_Tracer()
         res2 = tr2.iterative_tracer(ls, meshes, **params)
         assert set(tr2.stats["tc_warps"]) == {variant}
+        assert tr2._lib.lpcl_search_launch_count(tr2._scene) == 2  # no second pass
         util.assert_results_equal(list(res2), res1, "epilogue variant %d" % variant)
     rc = tr2._lib.lpcl_scene_set_tc_warps(tr2._scene, 12)
     assert rc != 0 and b"warps" in tr2._lib.lpcl_last_error()
