@@ -82,7 +82,10 @@ int32_t lpcl_scene_mesh_count(const lpcl_scene *scene);
 int64_t lpcl_scene_device_bytes(const lpcl_scene *scene); /* memory owned by the handle */
 
 /* Bytes of caller-owned device scratch the search needs for n rays: per (mesh, ray) one packed
- * 64-bit (nearest t, triangle) key and one 32-bit crossing count, mesh-major. */
+ * 64-bit (nearest t, triangle) key and one 32-bit crossing count, mesh-major; plus the record buffer through which
+ * the default (deferred-flag) search hands flagged (ray, 16-triangle chunk) pairs to its second pass: 8 bytes per
+ * record, LPCL_REC_PER_RAY records per ray (environment, read once per process; default 32, i.e. 256 bytes per ray;
+ * records that do not fit are evaluated inside the sweep kernel - slower, same results). */
 int64_t lpcl_scratch_bytes(const lpcl_scene *scene, int64_t n_rays);
 
 /* ---------------------------------------------------------------- reference-seam kernels
