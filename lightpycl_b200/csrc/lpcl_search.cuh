@@ -103,36 +103,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
-// the same without suspending: mbarrier.test_wait polled (for a warp whose reaction time is on the critical path)
-__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LPCL_SPIN:\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LPCL_SPUN;\n"
-        "bra LPCL_SPIN;\n"
-        "LPCL_SPUN:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// try_wait with the default (implementation-chosen) suspend time
-__device__ __forceinline__ void mbar_wait_short(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LPCL_WS:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LPCL_WSD;\n"
-        "bra LPCL_WS;\n"
-        "LPCL_WSD:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_bulk(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
 {
